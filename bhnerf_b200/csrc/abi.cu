@@ -1,0 +1,193 @@
+// extern "C" entry points (include/bhnerf_b200.h): argument checking, workspace carving, chunking.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+void bh_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* bhnerf_last_error(void) { return g_err; }
+extern "C" int bhnerf_version(void) { return BHNERF_ABI_VERSION; }
+
+extern "C" int bhnerf_device_check(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  BH_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  BH_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  BH_REQUIRE(p.major == 10, "bhnerf_b200 is built for sm_100a only; device is sm_%d%d", p.major, p.minor);
+  return 0;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static FrameConsts frame_consts(const bhnerf_scene_t* sc) {
+  FrameConsts fc; fc.t_start_obs = sc->t_start_obs; fc.GM_c3 = sc->GM_c3; fc.t_injection = sc->t_injection;
+  fc.scale = sc->scale; return fc;
+}
+static int check_scene(const bhnerf_scene_t* sc, int Bt, int impl) {
+  BH_REQUIRE(sc && sc->packed, "scene is NULL / not prepacked");
+  BH_REQUIRE(sc->n_pad > 0 && sc->n_pad % 128 == 0 && sc->S >= 1 && sc->S <= 4, "scene: bad n_pad/S");
+  BH_REQUIRE(Bt > 0, "Bt must be > 0");
+  BH_REQUIRE(impl == BHNERF_IMPL_SIMT || impl == BHNERF_IMPL_TC, "unknown impl %d", impl);
+  BH_REQUIRE(sc->GM_c3 > 0.f && sc->scale > 0.f, "scene: GM_c3 and scale must be > 0");
+  return 0;
+}
+
+static size_t acts_bytes_per_frame(const bhnerf_scene_t* sc, int impl) {
+  return impl == BHNERF_IMPL_SIMT ? bh_simt_acts_floats_per_frame(sc->n_pad) * 4
+                                  : bh_tc_acts_bytes_per_frame(sc->n_pad);
+}
+extern "C" size_t bhnerf_acts_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
+  return acts_bytes_per_frame(sc, impl) * (size_t)Bt;
+}
+
+// fixed (frame-count independent) part of the backward workspace
+static size_t bwd_fixed_bytes(int impl) {
+  return impl == BHNERF_IMPL_SIMT ? align_up(BH_SIMT_WT_FLOATS * 4, 256) : align_up(bh_tc_ws_bytes(), 256);
+}
+// per-frame scratch of the backward beyond saved activations
+static size_t bwd_frame_bytes(const bhnerf_scene_t* sc, int impl) {
+  return impl == BHNERF_IMPL_SIMT ? bh_simt_delta_floats_per_frame(sc->n_pad) * 4 : 0;
+}
+
+// TC variant needs scratch for the bf16 weight images; the SIMT variant ignores it.
+extern "C" size_t bhnerf_fwd_workspace_bytes(int32_t impl) {
+  return impl == BHNERF_IMPL_TC ? align_up(bh_tc_ws_bytes(), 256) : 0;
+}
+extern "C" int bhnerf_render_fwd(const bhnerf_scene_t* sc, const float* params, const float* t_frames,
+                                    int32_t Bt, float* images, float* e_out, void* acts_out, void* workspace,
+                                    size_t workspace_bytes, int32_t impl, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int r = check_scene(sc, Bt, impl)) return r;
+  BH_REQUIRE(params && t_frames && images && e_out, "render_fwd: NULL argument (e_out is required)");
+  PackedView v = bh_view(sc);
+  FrameConsts fc = frame_consts(sc);
+  if (impl == BHNERF_IMPL_SIMT) {
+    if (int r = bh_simt_fwd(v, fc, params, t_frames, Bt, e_out, (float*)acts_out, st)) return r;
+  } else {
+    BH_REQUIRE(workspace && workspace_bytes >= bhnerf_fwd_workspace_bytes(impl), "render_fwd: workspace too small");
+    if (int r = bh_tc_prepare_weights(params, workspace, st)) return r;
+    if (int r = bh_tc_fwd(v, fc, workspace, params, t_frames, Bt, e_out, acts_out, st)) return r;
+  }
+  return bh_launch_ray_integrate(v, e_out, Bt, images, st);
+}
+
+extern "C" size_t bhnerf_bwd_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
+  // enough for ONE frame of recompute; more lets the backward chunk more frames per launch
+  (void)Bt;
+  return bwd_fixed_bytes(impl) + acts_bytes_per_frame(sc, impl) + bwd_frame_bytes(sc, impl) +
+         (size_t)sc->n_pad * 4 + 1024;
+}
+
+extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, const float* t_frames, int32_t Bt,
+                                 const float* d_images, const float* e_saved, const void* acts_saved,
+                                 float* d_params, void* workspace, size_t workspace_bytes, int32_t impl,
+                                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int r = check_scene(sc, Bt, impl)) return r;
+  BH_REQUIRE(params && t_frames && d_images && d_params && workspace, "render_bwd: NULL argument");
+  PackedView v = bh_view(sc);
+  FrameConsts fc = frame_consts(sc);
+  char* ws = (char*)workspace;
+  size_t fixed = bwd_fixed_bytes(impl);
+  BH_REQUIRE(workspace_bytes >= fixed, "render_bwd: workspace too small");
+  char* p = ws + fixed;
+  size_t avail = workspace_bytes - fixed;
+  size_t per_frame = bwd_frame_bytes(sc, impl) + (acts_saved ? 0 : acts_bytes_per_frame(sc, impl)) +
+                     (e_saved && acts_saved ? 0 : (size_t)sc->n_pad * 4);
+  int Bc = per_frame ? (int)(avail / per_frame) : Bt;
+  if (Bc > Bt) Bc = Bt;
+  BH_REQUIRE(Bc >= 1, "render_bwd: workspace (%zu B) cannot hold one frame (%zu B + %zu B fixed)",
+             workspace_bytes, per_frame, fixed);
+  BH_CHECK_CUDA(cudaMemsetAsync(d_params, 0, BHNERF_N_PARAMS * sizeof(float), st));
+  if (impl == BHNERF_IMPL_TC) { if (int r = bh_tc_prepare_weights(params, ws, st)) return r; }
+  bool recompute = (acts_saved == nullptr) || (e_saved == nullptr);
+  for (int b0 = 0; b0 < Bt; b0 += Bc) {
+    int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
+    char* q = p;
+    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl) * nb;
+    const void* acts = acts_saved ? (const char*)acts_saved + acts_bytes_per_frame(sc, impl) * b0 : nullptr;
+    const float* e = e_saved ? e_saved + (size_t)b0 * sc->n_pad : nullptr;
+    if (recompute) {
+      void* acts_ws = q; q += acts_bytes_per_frame(sc, impl) * nb;
+      float* e_ws = (float*)q;
+      if (impl == BHNERF_IMPL_SIMT) {
+        if (int r = bh_simt_fwd(v, fc, params, t_frames + b0, nb, e_ws, (float*)acts_ws, st)) return r;
+      } else {
+        if (int r = bh_tc_fwd(v, fc, ws, params, t_frames + b0, nb, e_ws, acts_ws, st)) return r;
+      }
+      acts = acts_ws; e = e_ws;
+    }
+    const float* dI = d_images + (size_t)b0 * sc->S * sc->P;
+    if (impl == BHNERF_IMPL_SIMT) {
+      if (int r = bh_simt_bwd(v, params, dI, nb, e, (const float*)acts, delta, (float*)ws, d_params, st)) return r;
+    } else {
+      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, d_params, st)) return r;
+    }
+  }
+  return 0;
+}
+
+// ---- fused train step for separable image losses ----
+static size_t train_frame_bytes(const bhnerf_scene_t* sc, int impl) {
+  return acts_bytes_per_frame(sc, impl) + bwd_frame_bytes(sc, impl) + (size_t)sc->n_pad * 4 +
+         (size_t)sc->S * sc->P * 4;
+}
+extern "C" size_t bhnerf_train_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
+  // all Bt frames in one chunk; smaller workspaces are accepted down to one frame
+  return bwd_fixed_bytes(impl) + train_frame_bytes(sc, impl) * (size_t)Bt + 1024;
+}
+
+int bh_loss_image_accum(const float* images, const float* target, const float* sigma, const float* offset,
+                        float loss_scale, int kind, int Bt, int S, int P, float* loss, float* d_images,
+                        cudaStream_t st);
+
+extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* params, const float* t_frames,
+                                       int32_t Bt, const float* target, const float* sigma, const float* offset,
+                                       float loss_scale, int32_t kind, float* loss, float* images, float* d_params,
+                                       void* workspace, size_t workspace_bytes, int32_t impl, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int r = check_scene(sc, Bt, impl)) return r;
+  BH_REQUIRE(params && t_frames && target && sigma && offset && loss && images && d_params && workspace,
+             "train_step_image: NULL argument");
+  BH_REQUIRE(kind == BHNERF_LOSS_FULL || kind == BHNERF_LOSS_LC, "image dtype (%d) not supported", kind);
+  PackedView v = bh_view(sc);
+  FrameConsts fc = frame_consts(sc);
+  char* ws = (char*)workspace;
+  size_t fixed = bwd_fixed_bytes(impl);
+  size_t per_frame = train_frame_bytes(sc, impl);
+  BH_REQUIRE(workspace_bytes >= fixed + per_frame, "train_step_image: workspace (%zu B) cannot hold one frame (%zu B)",
+             workspace_bytes, fixed + per_frame);
+  int Bc = (int)((workspace_bytes - fixed) / per_frame);
+  if (Bc > Bt) Bc = Bt;
+  BH_CHECK_CUDA(cudaMemsetAsync(d_params, 0, BHNERF_N_PARAMS * sizeof(float), st));
+  BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  if (impl == BHNERF_IMPL_TC) { if (int r = bh_tc_prepare_weights(params, ws, st)) return r; }
+  size_t tstride = (kind == BHNERF_LOSS_FULL) ? (size_t)sc->S * sc->P : (size_t)sc->S;
+  for (int b0 = 0; b0 < Bt; b0 += Bc) {
+    int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
+    char* q = ws + fixed;
+    void* acts = q; q += acts_bytes_per_frame(sc, impl) * nb;
+    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl) * nb;
+    float* e = (float*)q; q += (size_t)sc->n_pad * 4 * nb;
+    float* dI = (float*)q;
+    float* img = images + (size_t)b0 * sc->S * sc->P;
+    if (impl == BHNERF_IMPL_SIMT) {
+      if (int r = bh_simt_fwd(v, fc, params, t_frames + b0, nb, e, (float*)acts, st)) return r;
+    } else {
+      if (int r = bh_tc_fwd(v, fc, ws, params, t_frames + b0, nb, e, acts, st)) return r;
+    }
+    if (int r = bh_launch_ray_integrate(v, e, nb, img, st)) return r;
+    if (int r = bh_loss_image_accum(img, target + b0 * tstride, sigma + b0 * tstride, offset + b0 * tstride,
+                                    loss_scale, kind, nb, sc->S, sc->P, loss, dI, st)) return r;
+    if (impl == BHNERF_IMPL_SIMT) {
+      if (int r = bh_simt_bwd(v, params, dI, nb, e, (const float*)acts, delta, (float*)ws, d_params, st)) return r;
+    } else {
+      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, d_params, st)) return r;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,321 @@
+// Ray integral, loss heads (image / lightcurve / visibility) and the Adam update.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// images[b,s,p] = sum_{i in ray p} e[b,i] * w[s,i]        (kgeo.radiative_trasfer, kgeo.py:618-621)
+// one thread per (b,p); the CSR ranges of neighbouring rays are adjacent in memory. Deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void ray_integrate_kernel(PackedView v, const float* __restrict__ e, int Bt,
+                                     float* __restrict__ images) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = blockIdx.y;
+  if (p >= v.P) return;
+  int i0 = v.row_ptr[p], i1 = v.row_ptr[p + 1];
+  const float* eb = e + (size_t)b * v.n_pad;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = i0; i < i1; ++i) {
+    float ev = eb[i];
+    for (int s = 0; s < v.S; ++s) acc[s] += ev * v.w[(size_t)s * v.n_pad + i];
+  }
+  for (int s = 0; s < v.S; ++s) images[((size_t)b * v.S + s) * v.P + p] = acc[s];
+}
+
+int bh_launch_ray_integrate(const PackedView& v, const float* e, int Bt, float* images, cudaStream_t st) {
+  dim3 grid((v.P + 127) / 128, Bt);
+  ray_integrate_kernel<<<grid, 128, 0, st>>>(v, e, Bt, images);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// image losses (network.py:476-484)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (wid == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sh[0] = v;
+  __syncthreads();
+  return sh[0];
+}
+
+// 'full': loss = scale * sum |(I - t - off)/sigma|^2 ; dI = 2*scale*(I - t - off)/sigma^2
+__global__ void loss_full_kernel(const float* __restrict__ I, const float* __restrict__ t,
+                                 const float* __restrict__ sg, const float* __restrict__ off, float scale,
+                                 size_t n, float* __restrict__ loss, float* __restrict__ dI) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float r = (I[i] - t[i] - off[i]) / sg[i];
+    acc += r * r;
+    dI[i] = 2.f * scale * r / sg[i];
+  }
+  float tot = block_reduce_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, scale * tot);
+}
+
+// 'lc': lightcurve[b,s] = sum_p I[b,s,p]; loss = scale*sum |(lc - t - off)/sigma|^2; one block per (b,s)
+__global__ void loss_lc_kernel(const float* __restrict__ I, const float* __restrict__ t,
+                               const float* __restrict__ sg, const float* __restrict__ off, float scale,
+                               int P, float* __restrict__ loss, float* __restrict__ dI) {
+  __shared__ float sh[32];
+  int bs = blockIdx.x;
+  const float* row = I + (size_t)bs * P;
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) acc += row[p];
+  float lc = block_reduce_sum(acc, sh);
+  float r = (lc - t[bs] - off[bs]) / sg[bs];
+  float d = 2.f * scale * r / sg[bs];
+  for (int p = threadIdx.x; p < P; p += blockDim.x) dI[(size_t)bs * P + p] = d;
+  if (threadIdx.x == 0) atomicAdd(loss, scale * r * r);
+}
+
+// accumulates into *loss (caller zeroes it)
+int bh_loss_image_accum(const float* images, const float* target, const float* sigma, const float* offset,
+                        float loss_scale, int kind, int Bt, int S, int P, float* loss, float* d_images,
+                        cudaStream_t st) {
+  if (kind == BHNERF_LOSS_FULL) {
+    size_t n = (size_t)Bt * S * P;
+    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
+    loss_full_kernel<<<blocks, 256, 0, st>>>(images, target, sigma, offset, loss_scale, n, loss, d_images);
+  } else {
+    loss_lc_kernel<<<Bt * S, 256, 0, st>>>(images, target, sigma, offset, loss_scale, P, loss, d_images);
+  }
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhnerf_loss_image(const float* images, const float* target, const float* sigma,
+                                 const float* offset, float loss_scale, int32_t kind, int32_t Bt, int32_t S,
+                                 int32_t P, float* loss, float* d_images, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_REQUIRE(kind == BHNERF_LOSS_FULL || kind == BHNERF_LOSS_LC, "loss_image: image dtype (%d) not supported", kind);
+  BH_REQUIRE(images && target && sigma && offset && loss && d_images, "loss_image: NULL argument");
+  BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  return bh_loss_image_accum(images, target, sigma, offset, loss_scale, kind, Bt, S, P, loss, d_images, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// visibility head (network.py:542-564): vis[b,v] = sum_p A[b,v,p] * I[b,p], complex64 A.
+// HBM-bound stream of A (8*V*P bytes per frame per pass): one warp per (b,v) row, float4 loads.
+// ---------------------------------------------------------------------------------------------
+__global__ void vis_fwd_kernel(const float2* __restrict__ A, const float* __restrict__ I, int V, int P,
+                               float2* __restrict__ vis) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.y;
+  if (warp >= V) return;
+  const float2* row = A + ((size_t)b * V + warp) * P;
+  const float* img = I + (size_t)b * P;
+  float re = 0.f, im = 0.f;
+  if ((P & 1) == 0) {
+    const float4* row4 = (const float4*)row;
+    const float2* img2 = (const float2*)img;
+    for (int q = lane; q < P / 2; q += 32) {
+      float4 a = __ldcs(row4 + q);          // streamed once: evict-first
+      float2 x = img2[q];
+      re += a.x * x.x + a.z * x.y;
+      im += a.y * x.x + a.w * x.y;
+    }
+  } else {
+    for (int p = lane; p < P; p += 32) { float2 a = row[p]; float x = img[p]; re += a.x * x; im += a.y * x; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if (lane == 0) vis[(size_t)b * V + warp] = make_float2(re, im);
+}
+
+// d_images[b,p] = sum_v Re(conj(A[b,v,p]) * d_vis[b,v]) = sum_v A.re*dv.re + A.im*dv.im
+__global__ void vis_bwd_kernel(const float2* __restrict__ A, const float2* __restrict__ dvis, int V, int P,
+                               float* __restrict__ dI) {
+  extern __shared__ float2 dv_s[];
+  int b = blockIdx.y;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) dv_s[v] = dvis[(size_t)b * V + v];
+  __syncthreads();
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float2* col = A + (size_t)b * V * P + p;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int v = 0; v < V; ++v) {
+    float2 a = __ldcs(col + (size_t)v * P);
+    acc += a.x * dv_s[v].x + a.y * dv_s[v].y;
+  }
+  dI[(size_t)b * P + p] = acc;
+}
+
+// 'vis': chisq = sum (|vis - t|/sigma)^2 ; 'amp': chisq = sum |(|vis| - t)/sigma|^2
+__global__ void loss_vis_kernel(const float2* __restrict__ vis, const float* __restrict__ target,
+                                const float* __restrict__ sg, float scale, int kind, int n,
+                                float* __restrict__ loss, float2* __restrict__ dvis) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float2 v = vis[i];
+    float s2 = sg[i] * sg[i];
+    if (kind == BHNERF_LOSS_VIS) {
+      float2 t = ((const float2*)target)[i];
+      float dr = v.x - t.x, di = v.y - t.y;
+      acc += (dr * dr + di * di) / s2;
+      dvis[i] = make_float2(2.f * scale * dr / s2, 2.f * scale * di / s2);
+    } else {
+      float amp = sqrtf(v.x * v.x + v.y * v.y);
+      float r = amp - target[i];
+      acc += r * r / s2;
+      float k = (amp > 0.f) ? 2.f * scale * r / (s2 * amp) : 0.f;
+      dvis[i] = make_float2(k * v.x, k * v.y);
+    }
+  }
+  float tot = block_reduce_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, scale * tot);
+}
+
+extern "C" int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, int32_t V, int32_t P, float* vis,
+                              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((V * 32 + 255) / 256, Bt);
+  vis_fwd_kernel<<<grid, 256, 0, st>>>((const float2*)A, images, V, P, (float2*)vis);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhnerf_loss_vis(const float* vis, const float* target, const float* sigma, float loss_scale,
+                               int32_t kind, int32_t Bt, int32_t V, float* loss, float* d_vis, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_REQUIRE(kind == BHNERF_LOSS_VIS || kind == BHNERF_LOSS_AMP, "loss_vis: eht dtype (%d) not supported", kind);
+  BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  int n = Bt * V;
+  int blocks = (n + 255) / 256; if (blocks > 592) blocks = 592;
+  loss_vis_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, kind, n, loss,
+                                          (float2*)d_vis);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, int32_t V, int32_t P,
+                              float* d_images, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_REQUIRE((size_t)V * sizeof(float2) <= 48 * 1024, "vis_bwd: V=%d too large", V);
+  dim3 grid((P + 255) / 256, Bt);
+  vis_bwd_kernel<<<grid, 256, V * sizeof(float2), st>>>((const float2*)A, (const float2*)d_vis, V, P, d_images);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optax.adam + polynomial_schedule(power=1) (network.py:173-174, :621)
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
+                            float* __restrict__ nu, int n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2, float gscale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * gscale;
+  float m = b1 * mu[i] + (1.f - b1) * gi;
+  float v = b2 * nu[i] + (1.f - b2) * gi * gi;
+  mu[i] = m; nu[i] = v;
+  float mh = m / bc1, vh = v / bc2;
+  p[i] = p[i] - lr * mh / (sqrtf(vh) + eps);
+}
+
+extern "C" int bhnerf_adam_step(float* params, const float* grads, float* mu, float* nu, int32_t n,
+                                int32_t count, float lr_init, float lr_final, int32_t transition_steps,
+                                float b1, float b2, float eps, float grad_scale, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_REQUIRE(transition_steps > 0, "adam: transition_steps must be > 0");
+  int c = count < 0 ? 0 : (count > transition_steps ? transition_steps : count);
+  double frac = 1.0 - (double)c / (double)transition_steps;
+  float lr = (float)((double)(lr_init - lr_final) * frac + (double)lr_final);
+  double t = (double)count + 1.0;
+  float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
+  adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(params, grads, mu, nu, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone dense stages (the reference exposes them as public functions; inside the render
+// kernels they are fused).  Elementwise / short reductions, HBM-bound.
+// ---------------------------------------------------------------------------------------------
+// emission.velocity_warp_coords (emission.py:143-211): out[b,i,:] = R_z(-theta) coords[:,i], NaN where t_M<0
+__global__ void warp_coords_kernel(const float* __restrict__ coords, const float* __restrict__ Omega,
+                                   const float* __restrict__ t_geos, size_t N, const float* __restrict__ t_frames,
+                                   FrameConsts fc, float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b = blockIdx.y;
+  if (i >= N) return;
+  float tfc = bh_frame_time(t_frames[b], fc);
+  float tM = __fsub_rn(__fadd_rn(tfc, t_geos[i]), fc.t_injection);
+  float x = coords[i], y = coords[N + i], z = coords[2 * N + i];
+  float* o = out + ((size_t)b * N + i) * 3;
+  if (tM < 0.0f) { float nan = __int_as_float(0x7fc00000); o[0] = nan; o[1] = nan; o[2] = nan; return; }
+  float sn, cs;
+  sincosf(__fmul_rn(tM, Omega[i]), &sn, &cs);
+  o[0] = x * cs + y * sn; o[1] = y * cs - x * sn; o[2] = z;
+}
+extern "C" int bhnerf_velocity_warp_coords(const float* coords, const float* Omega, const float* t_geos, int64_t N,
+                                           const float* t_frames, int32_t Bt, float t_start_obs, float GM_c3,
+                                           float t_injection, float* out, void* stream) {
+  BH_REQUIRE(coords && Omega && t_geos && t_frames && out && N > 0 && Bt > 0 && GM_c3 > 0.f, "velocity_warp_coords: bad argument");
+  FrameConsts fc; fc.t_start_obs = t_start_obs; fc.GM_c3 = GM_c3; fc.t_injection = t_injection; fc.scale = 1.f;
+  dim3 grid((unsigned)((N + 255) / 256), Bt);
+  warp_coords_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(coords, Omega, t_geos, (size_t)N, t_frames, fc, out);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// emission.fill_unsupervised_emission (emission.py:343-374), in place on e[R,N] with coords[3,N]
+__global__ void fill_unsupervised_kernel(float* __restrict__ e, const float* __restrict__ coords, size_t N,
+                                         float rmin2, float rmax2, float zw, float fill) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float x = coords[i], y = coords[N + i], z = coords[2 * N + i];
+  float r2 = x * x + y * y + z * z;
+  if ((r2 < rmin2) || (r2 > rmax2) || (fabsf(z) > zw)) e[(size_t)blockIdx.y * N + i] = fill;
+}
+extern "C" int bhnerf_fill_unsupervised_emission(float* emission, const float* coords, int32_t R, int64_t N,
+                                                 float rmin, float rmax, float z_width, float fill_value,
+                                                 void* stream) {
+  BH_REQUIRE(emission && coords && R > 0 && N > 0, "fill_unsupervised_emission: bad argument");
+  dim3 grid((unsigned)((N + 255) / 256), R);
+  fill_unsupervised_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(emission, coords, (size_t)N, rmin * rmin,
+                                                                   rmax * rmax, z_width, fill_value);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// kgeo.radiative_trasfer (kgeo.py:595-622): out[r,p] = sum_k g^2 * e[r,p,k] * dtau * Sigma; one warp per (r,p)
+__global__ void radiative_transfer_kernel(const float* __restrict__ e, const float* __restrict__ g,
+                                          const float* __restrict__ dtau, const float* __restrict__ Sigma,
+                                          int P, int G, float* __restrict__ out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int r = blockIdx.y;
+  if (warp >= P) return;
+  const float* er = e + ((size_t)r * P + warp) * G;
+  size_t base = (size_t)warp * G;
+  float acc = 0.f;
+  for (int k = lane; k < G; k += 32) { float gg = g[base + k]; acc += gg * gg * er[k] * dtau[base + k] * Sigma[base + k]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[(size_t)r * P + warp] = acc;
+}
+extern "C" int bhnerf_radiative_transfer(const float* emission, const float* g, const float* dtau, const float* Sigma,
+                                         int32_t R, int32_t P, int32_t G, float* out, void* stream) {
+  BH_REQUIRE(emission && g && dtau && Sigma && out && R > 0 && P > 0 && G > 0, "radiative_transfer: bad argument");
+  dim3 grid((P * 32 + 255) / 256, R);
+  radiative_transfer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(emission, g, dtau, Sigma, P, G, out);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

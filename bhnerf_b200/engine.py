@@ -1,0 +1,264 @@
+"""Host-side plumbing above the C ABI: device buffers (torch tensors), streams and workspaces.
+
+PyTorch is used for device memory and streams only; every compute step below is a call into
+libbhnerf_b200.so (hand-written CUDA for sm_100a).  Nothing here falls back to torch math."""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IMPL_SIMT, IMPL_TC, LOSS_KINDS, N_PARAMS, Scene, check
+
+
+def resolve_impl(impl=None):
+    impl = impl if impl is not None else os.environ.get('BHNERF_IMPL', 'auto')
+    if isinstance(impl, int):
+        return impl
+    impl = str(impl).lower()
+    if impl in ('tc', 'tcgen05', '1'):
+        return IMPL_TC
+    if impl in ('simt', 'fp32', '0'):
+        return IMPL_SIMT
+    if impl == 'auto':
+        return DEFAULT_IMPL
+    raise ValueError('unknown impl %r' % (impl,))
+
+
+DEFAULT_IMPL = IMPL_SIMT   # switched to IMPL_TC once the tcgen05 family is parity-green on hardware
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32)), device=device)
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only per-device scratch (allocated off the hot path after the first step)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[key] = ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    return ws
+
+
+class PackedScene:
+    """Prepacked, frame-independent scene: the non-optimised arguments of network.raytracing_args
+    (bhnerf/network.py:850-894) + the NeRF_Predictor domain constants (bhnerf/network.py:147-157)."""
+
+    def __init__(self, coords, Omega, J, g, dtau, Sigma, t_geos, t_start_obs, t_injection, scale, rmin, rmax,
+                 z_width, GM_c3, device=None):
+        lib = _lib.load()
+        device = torch.device(device if device is not None else 'cuda')
+        coords = _dev_f32(coords, device)
+        assert coords.shape[0] == 3, 'coords must be (3, ...)'
+        self.image_shape = tuple(coords.shape[1:-1])
+        G = coords.shape[-1]
+        P = int(np.prod(self.image_shape)) if self.image_shape else 1
+        coords = coords.reshape(3, P, G)
+
+        def field(a):
+            a = _dev_f32(a, device)
+            if a.dim() == 0:
+                a = a.expand(P, G)
+            return a.reshape(P, G).contiguous()
+        Omega, g, dtau, Sigma, t_geos = [field(a) for a in (Omega, g, dtau, Sigma, t_geos)]
+        if J is None or np.isscalar(J) or (hasattr(J, 'ndim') and J.ndim == 0):
+            assert J is None or float(J) == 1.0, 'scalar J must be 1.0 (network.py:874 default)'
+            Jd, S = None, 1
+            self.polarized = False
+        else:
+            Jd = _dev_f32(J, device)
+            S = Jd.shape[0]
+            Jd = Jd.reshape(S, P, G).contiguous()
+            self.polarized = True
+        nbytes = lib.bhnerf_packed_bytes(P, G, S)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        sc = Scene()
+        with torch.cuda.device(device):
+            check(lib.bhnerf_prepack(_ptr(coords), _ptr(Omega), _ptr(g), _ptr(dtau), _ptr(Sigma), _ptr(t_geos),
+                                     _ptr(Jd), P, G, S, float(rmin), float(rmax), float(z_width), _ptr(packed),
+                                     nbytes, C.byref(sc), _stream()))
+        # shrink to what is used: row_ptr + (7+S) arrays of n_pad
+        used = ((P + 1 + 127) // 128 * 128) * 4 + (7 + S) * sc.n_pad * 4
+        self.packed = packed[:used].clone()
+        del packed
+        sc.packed = self.packed.data_ptr()
+        sc.t_start_obs = float(t_start_obs); sc.GM_c3 = float(GM_c3)
+        sc.t_injection = float(t_injection); sc.scale = float(scale)
+        self.struct = sc
+        self.device = device
+        self.P, self.G, self.S = P, G, S
+        self.n_active, self.n_pad = sc.n_active, sc.n_pad
+        self.rmin, self.rmax, self.z_width = float(rmin), float(rmax), float(z_width)
+
+    @property
+    def ref(self):
+        return C.byref(self.struct)
+
+    def _int_array(self, which):
+        off = ((self.P + 1 + 127) // 128 * 128) * 4 + (5 + self.S + which) * self.n_pad * 4
+        return self.packed[off: off + self.n_pad * 4].view(torch.int32)
+
+    @property
+    def row_ptr(self):
+        return self.packed[: (self.P + 1) * 4].view(torch.int32)
+
+    @property
+    def ray_index(self):
+        """[n_pad] ray of each compacted sample (-1 = padding)."""
+        return self._int_array(0)
+
+    @property
+    def dense_index(self):
+        """[n_active] flat index ray*G + k of each compacted sample in the dense (P,G) arrays."""
+        n = self.n_active
+        return self._int_array(0)[:n].long() * self.G + self._int_array(1)[:n].long()
+
+
+def render_fwd(scene, params, t_frames, impl=None, save_acts=False):
+    """images [Bt,S,P], e [Bt,n_pad], acts (or None).  C ABI: bhnerf_render_fwd."""
+    lib = _lib.load(); impl = resolve_impl(impl)
+    dev = scene.device
+    params = _dev_f32(params, dev); t_frames = _dev_f32(t_frames, dev).reshape(-1)
+    assert params.numel() == N_PARAMS
+    Bt = t_frames.numel()
+    images = torch.empty((Bt, scene.S, scene.P), dtype=torch.float32, device=dev)
+    e = torch.empty((Bt, scene.n_pad), dtype=torch.float32, device=dev)
+    acts = None
+    if save_acts:
+        acts = torch.empty(lib.bhnerf_acts_bytes(scene.ref, Bt, impl), dtype=torch.uint8, device=dev)
+    wsb = lib.bhnerf_fwd_workspace_bytes(impl)
+    ws = workspace(wsb, dev) if wsb else None
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_render_fwd(scene.ref, _ptr(params), _ptr(t_frames), Bt, _ptr(images), _ptr(e), _ptr(acts),
+                                    _ptr(ws), wsb, impl, _stream()))
+    return images, e, acts
+
+
+def render_bwd(scene, params, t_frames, d_images, e=None, acts=None, impl=None, max_workspace=None):
+    """d_params [55169].  C ABI: bhnerf_render_bwd (recomputes what is not passed in)."""
+    lib = _lib.load(); impl = resolve_impl(impl)
+    dev = scene.device
+    params = _dev_f32(params, dev); t_frames = _dev_f32(t_frames, dev).reshape(-1)
+    d_images = _dev_f32(d_images, dev)
+    Bt = t_frames.numel()
+    assert d_images.numel() == Bt * scene.S * scene.P
+    one = lib.bhnerf_bwd_workspace_bytes(scene.ref, Bt, impl)
+    full = one + (one - 1024) * (Bt - 1)
+    nbytes = full if max_workspace is None else max(one, min(full, int(max_workspace)))
+    ws = workspace(nbytes, dev)
+    grads = torch.empty(N_PARAMS, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_render_bwd(scene.ref, _ptr(params), _ptr(t_frames), Bt, _ptr(d_images), _ptr(e), _ptr(acts),
+                                    _ptr(grads), _ptr(ws), nbytes, impl, _stream()))
+    return grads
+
+
+def loss_image(images, target, sigma, offset, scale, kind):
+    """(loss[1], d_images).  C ABI: bhnerf_loss_image (loss_fn_image, bhnerf/network.py:476-484)."""
+    lib = _lib.load()
+    dev = images.device
+    Bt, S, P = images.shape
+    target, sigma, offset = [_dev_f32(a, dev) for a in (target, sigma, offset)]
+    k = LOSS_KINDS[kind] if isinstance(kind, str) else kind
+    want = Bt * S * P if k == 0 else Bt * S
+    assert target.numel() == want and sigma.numel() == want and offset.numel() == want, 'target shape mismatch'
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dI = torch.empty_like(images)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_loss_image(_ptr(images), _ptr(target), _ptr(sigma), _ptr(offset), float(scale), k, Bt, S, P,
+                                    _ptr(loss), _ptr(dI), _stream()))
+    return loss, dI
+
+
+def _c64(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.complex64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.complex64)), device=dev)
+
+
+def vis_fwd(A, images):
+    """vis [Bt,V] complex64 = A[b] @ vec(I[b])  (bhnerf/network.py:542-544).  images [Bt,1,P] or [Bt,P]."""
+    lib = _lib.load(); dev = images.device
+    Bt, V, P = A.shape
+    vis = torch.empty((Bt, V), dtype=torch.complex64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_vis_fwd(_ptr(A), _ptr(images), Bt, V, P, _ptr(vis), _stream()))
+    return vis
+
+
+def loss_vis(vis, target, sigma, scale, kind):
+    lib = _lib.load(); dev = vis.device
+    Bt, V = vis.shape
+    k = LOSS_KINDS[kind] if isinstance(kind, str) else kind
+    target = _c64(target, dev) if k == LOSS_KINDS['vis'] else _dev_f32(target, dev)
+    sigma = _dev_f32(sigma, dev)
+    assert target.numel() == Bt * V and sigma.numel() == Bt * V
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dvis = torch.empty_like(vis)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_loss_vis(_ptr(vis), _ptr(target), _ptr(sigma), float(scale), k, Bt, V, _ptr(loss), _ptr(dvis),
+                                  _stream()))
+    return loss, dvis
+
+
+def vis_bwd(A, dvis, P):
+    lib = _lib.load(); dev = dvis.device
+    Bt, V = dvis.shape
+    dI = torch.empty((Bt, 1, P), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_vis_bwd(_ptr(A), _ptr(dvis), Bt, V, P, _ptr(dI), _stream()))
+    return dI
+
+
+def train_step_image(scene, params, t_frames, target, sigma, offset, scale, kind, impl=None, max_workspace=None,
+                     out=None):
+    """Fused fwd -> ray integral -> loss -> bwd.  Returns (loss[1], images [Bt,S,P], grads [55169]).
+    C ABI: bhnerf_train_step_image.  All inputs must already be device tensors for the hot loop."""
+    lib = _lib.load(); impl = resolve_impl(impl)
+    dev = scene.device
+    params = _dev_f32(params, dev); t_frames = _dev_f32(t_frames, dev).reshape(-1)
+    target, sigma, offset = [_dev_f32(a, dev) for a in (target, sigma, offset)]
+    Bt = t_frames.numel()
+    k = LOSS_KINDS[kind] if isinstance(kind, str) else kind
+    want = Bt * scene.S * scene.P if k == 0 else Bt * scene.S
+    assert target.numel() == want and sigma.numel() == want and offset.numel() == want, 'target shape mismatch'
+    full = lib.bhnerf_train_workspace_bytes(scene.ref, Bt, impl)
+    one = lib.bhnerf_train_workspace_bytes(scene.ref, 1, impl)
+    nbytes = full if max_workspace is None else max(one, min(full, int(max_workspace)))
+    ws = workspace(nbytes, dev)
+    if out is None:
+        out = (torch.empty(1, dtype=torch.float32, device=dev),
+               torch.empty((Bt, scene.S, scene.P), dtype=torch.float32, device=dev),
+               torch.empty(N_PARAMS, dtype=torch.float32, device=dev))
+    loss, images, grads = out
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_train_step_image(scene.ref, _ptr(params), _ptr(t_frames), Bt, _ptr(target), _ptr(sigma),
+                                          _ptr(offset), float(scale), k, _ptr(loss), _ptr(images), _ptr(grads),
+                                          _ptr(ws), nbytes, impl, _stream()))
+    return loss, images, grads
+
+
+def adam_step(params, grads, mu, nu, count, lr_init=1e-4, lr_final=1e-6, num_iters=5000, b1=0.9, b2=0.999,
+              eps=1e-8, grad_scale=1.0):
+    """In-place optax.adam + linear schedule on the flat buffers.  C ABI: bhnerf_adam_step."""
+    lib = _lib.load()
+    with torch.cuda.device(params.device):
+        check(lib.bhnerf_adam_step(_ptr(params), _ptr(grads), _ptr(mu), _ptr(nu), params.numel(), int(count),
+                                   float(lr_init), float(lr_final), int(num_iters), float(b1), float(b2), float(eps),
+                                   float(grad_scale), _stream()))
+    return params

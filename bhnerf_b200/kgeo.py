@@ -1,0 +1,56 @@
+"""Mirror of the hot-path functions of the reference's ``bhnerf/kgeo.py``."""
+import numpy as np
+import torch
+
+from . import _lib, engine
+from ._lib import check
+
+
+def radiative_trasfer(emission, g, dtau, Sigma, use_jax=False):
+    """bhnerf/kgeo.py:595-622 (sic): sum over the last axis of g^2 * emission * dtau * Sigma.
+    emission (..., *img, G) with g/dtau/Sigma (*img, G); returns a device tensor (..., *img)."""
+    lib = _lib.load()
+    dev = torch.device('cuda')
+    e = engine._dev_f32(emission, dev)
+    gg, dt, Sg = [engine._dev_f32(a, dev) for a in (g, dtau, Sigma)]
+    G = e.shape[-1]
+    P = int(np.prod(gg.shape[:-1])) if gg.dim() > 1 else 1
+    R = e.numel() // (P * G)
+    out = torch.empty((R, P), dtype=torch.float32, device=dev)
+    check(lib.bhnerf_radiative_transfer(engine._ptr(e), engine._ptr(gg.expand(gg.shape).contiguous()),
+                                        engine._ptr(dt.contiguous()), engine._ptr(Sg.contiguous()), R, P, G,
+                                        engine._ptr(out), engine._stream()))
+    return out.reshape(tuple(e.shape[:-1]))
+
+
+def _get(geos, k):
+    return np.asarray(geos[k] if hasattr(geos, '__getitem__') else getattr(geos, k), dtype=np.float64)
+
+
+def azimuthal_velocity_vector(geos, Omega):
+    """bhnerf/kgeo.py:199-223 (host, numpy): contravariant u^mu = (u^t, 0, 0, u^t*Omega) from the Kerr metric.
+    Returns an array (..., 4).  Setup-time helper (runs once per (spin, inclination))."""
+    r, th, a, M = _get(geos, 'r'), _get(geos, 'theta'), _get(geos, 'spin'), _get(geos, 'M')
+    Sigma = r ** 2 + a ** 2 * np.cos(th) ** 2
+    Delta = r ** 2 + a ** 2 - 2 * M * r
+    Xi = (r ** 2 + a ** 2) ** 2 - a ** 2 * Delta * np.sin(th) ** 2
+    g_tt = -(1 - 2 * M * r / Sigma)
+    g_phph = Xi * np.sin(th) ** 2 / Sigma
+    g_tph = -2 * M * a * r * np.sin(th) ** 2 / Sigma
+    Om = np.asarray(Omega, dtype=np.float64)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        ut = 1 / np.sqrt(-(g_tt + 2 * Om * g_tph + g_phph * Om ** 2))
+    z = np.zeros_like(ut)
+    return np.stack([ut, z, z, ut * Om], axis=-1)
+
+
+def doppler_factor(geos, umu, fillna=0.0):
+    """bhnerf/kgeo.py:225-248: g = E / -(k_mu u^mu); with u^r = u^theta = 0 only k_t = -E and
+    k_phi = E*lam survive (bhnerf/kgeo.py:111-114)."""
+    E, lam = _get(geos, 'E'), _get(geos, 'lam')
+    umu = np.asarray(umu, dtype=np.float64)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        g = E / -(-E * umu[..., 0] + E * lam * umu[..., 3])
+    if not ((isinstance(fillna, bool) and fillna is False) or fillna is None):
+        g = np.where(np.isnan(g), fillna, g)
+    return g

@@ -1,0 +1,360 @@
+"""Host-side mirror of the reference's ``bhnerf/network.py`` for the render/train hot path.
+
+Same names, argument order and error behaviour as the reference (file:line cited per function);
+arrays are numpy / torch instead of jax, and every compute step is a C-ABI call into
+libbhnerf_b200.so through :mod:`bhnerf_b200.engine`.  Only the default architecture the kernels
+are specialised for is accepted (net_depth=4, net_width=128, posenc_deg=3, relu, out_channel=1,
+do_skip=True: bhnerf/network.py:147-157) -- anything else raises, it does not fall back."""
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import constants, engine, utils
+from ._lib import N_PARAMS
+
+LAYER_SHAPES = [(21, 128), (128, 128), (128, 128), (149, 128), (128, 1)]
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter pytree <-> flat buffer (flax names params['MLP_0']['Dense_i']['kernel'|'bias'])
+# ------------------------------------------------------------------------------------------------
+def flatten_params(params):
+    d = params['MLP_0'] if 'MLP_0' in params else params
+    out = []
+    for i, (fi, fo) in enumerate(LAYER_SHAPES):
+        k = np.asarray(d['Dense_%d' % i]['kernel'], dtype=np.float32)
+        b = np.asarray(d['Dense_%d' % i]['bias'], dtype=np.float32)
+        if k.shape != (fi, fo) or b.shape != (fo,):
+            raise ValueError('Dense_%d has shape %s/%s, expected %s/%s' % (i, k.shape, b.shape, (fi, fo), (fo,)))
+        out += [k.reshape(-1), b.reshape(-1)]
+    return np.concatenate(out)
+
+
+def unflatten_params(flat):
+    flat = flat.detach().cpu().numpy() if isinstance(flat, torch.Tensor) else np.asarray(flat)
+    d, o = OrderedDict(), 0
+    for i, (fi, fo) in enumerate(LAYER_SHAPES):
+        k = flat[o:o + fi * fo].reshape(fi, fo).copy(); o += fi * fo
+        b = flat[o:o + fo].copy(); o += fo
+        d['Dense_%d' % i] = {'kernel': k, 'bias': b}
+    return {'MLP_0': d}
+
+
+class TrainState:
+    """Stand-in for flax ``TrainState`` (bhnerf/network.py:182): flat device buffers for params and the
+    Adam moments, ``step`` counter, and the schedule hyper-parameters of ``init_state``."""
+
+    def __init__(self, predictor, flat_params, num_iters, lr_init, lr_final, device):
+        self.predictor = predictor
+        self.apply_fn = predictor.apply
+        self.flat = torch.as_tensor(np.asarray(flat_params, dtype=np.float32), device=device).clone()
+        self.mu = torch.zeros_like(self.flat)
+        self.nu = torch.zeros_like(self.flat)
+        self.step = 0
+        self.num_iters, self.lr_init, self.lr_final = int(num_iters), float(lr_init), float(lr_final)
+
+    @property
+    def params(self):
+        return unflatten_params(self.flat)
+
+    def apply_gradients(self, grads, grad_scale=1.0):
+        """optax.adam + polynomial_schedule(lr_init, lr_final, 1, num_iters) (network.py:173-174,:621)."""
+        engine.adam_step(self.flat, grads, self.mu, self.nu, self.step, self.lr_init, self.lr_final,
+                         self.num_iters, grad_scale=grad_scale)
+        self.step += 1
+        return self
+
+    def state_dict(self):
+        return {'step': self.step, 'params': self.params, 'mu': self.mu.cpu().numpy(), 'nu': self.nu.cpu().numpy()}
+
+
+class NeRF_Predictor:
+    """bhnerf/network.py:124-252."""
+
+    def __init__(self, scale=1.0, rmin=0.0, rmax=np.inf, z_width=np.inf, posenc_deg=3, posenc_var=2e-5,
+                 net_depth=4, net_width=128, activation='relu', out_channel=1, do_skip=True):
+        if (posenc_deg, net_depth, net_width, out_channel, do_skip) != (3, 4, 128, 1, True) or \
+                activation not in ('relu', None) and getattr(activation, '__name__', '') != 'relu':
+            raise NotImplementedError('bhnerf_b200 kernels are specialised for the reference defaults '
+                                      '(posenc_deg=3, net_depth=4, net_width=128, relu, out_channel=1, do_skip=True)')
+        self.scale, self.rmin, self.rmax, self.z_width = float(scale), float(rmin), float(rmax), float(z_width)
+        self.posenc_deg, self.posenc_var, self.net_depth, self.net_width = posenc_deg, posenc_var, net_depth, net_width
+        self.out_channel, self.do_skip = out_channel, do_skip
+
+    def init_params(self, raytracing_args=None, seed=1):
+        """he_uniform kernels / zero biases (network.py:49-50, :159-169).  numpy Generator, not threefry."""
+        rng = np.random.default_rng(seed)
+        d = OrderedDict()
+        for i, (fi, fo) in enumerate(LAYER_SHAPES):
+            lim = math.sqrt(6.0 / fi)
+            d['Dense_%d' % i] = {'kernel': rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32),
+                                 'bias': np.zeros((fo,), dtype=np.float32)}
+        return {'MLP_0': d}
+
+    def init_state(self, params, num_iters=5000, lr_init=1e-4, lr_final=1e-6, lr_inject=None, checkpoint_dir='',
+                   device=None):
+        """network.py:171-189.  ``lr_inject`` (learnable t_injection) is dead code in the reference (:235)."""
+        if lr_inject:
+            raise NotImplementedError('lr_inject: the t_injection parameter is commented out in the reference '
+                                      '(bhnerf/network.py:235)')
+        device = torch.device(device if device is not None else 'cuda')
+        state = TrainState(self, flatten_params(params), num_iters, lr_init, lr_final, device)
+        if checkpoint_dir:
+            from .optimization import restore_checkpoint
+            restore_checkpoint(checkpoint_dir, state)
+        return state
+
+    def domain(self):
+        return dict(scale=self.scale, rmin=self.rmin, rmax=self.rmax, z_width=self.z_width)
+
+    def apply(self, variables, t_frames, t_units, coords, Omega, t_start_obs, t_geos, t_injection, impl=None):
+        """NeRF_Predictor.__call__ (network.py:191-237): emission on the given points, shape (Bt, *coords.shape[1:])
+        (no Bt axis for a scalar t_frames).  Runs the forward kernel with unit ray weights."""
+        params = variables['params'] if 'params' in variables else variables
+        flat = params if isinstance(params, torch.Tensor) else flatten_params(params)
+        coords = np.asarray(coords, dtype=np.float32)
+        pts_shape = coords.shape[1:]
+        c2 = coords.reshape(3, -1, 1) if coords.ndim == 2 else coords.reshape(3, -1, coords.shape[-1])
+        P, G = c2.shape[1], c2.shape[2]
+        ones = np.ones((P, G), dtype=np.float32)
+        Om = np.broadcast_to(np.asarray(Omega, dtype=np.float32), pts_shape).reshape(P, G)
+        tg = np.broadcast_to(np.asarray(t_geos, dtype=np.float32), pts_shape).reshape(P, G)
+        t_units = t_units if t_units is not None else None
+        GM_c3 = constants.GM_c3(t_units=t_units) if t_units is not None else 1.0
+        # domain fill is applied exactly as in the reference; samples it zeroes are simply not evaluated
+        scene = engine.PackedScene(c2, Om, 1.0, ones, ones, ones, tg, utils.time_value(t_start_obs, t_units or 'hr'),
+                                   float(t_injection), self.scale, self.rmin, self.rmax, self.z_width, GM_c3)
+        tf = np.atleast_1d(utils.time_value(t_frames, t_units or 'hr')).astype(np.float32)
+        _, e, _ = engine.render_fwd(scene, flat, tf, impl)
+        # scatter the compacted emission back to the dense point set (dead samples are exactly 0)
+        dense = torch.zeros((len(tf), P * G), dtype=torch.float32, device=scene.device)
+        if scene.n_active:
+            dense[:, scene.dense_index] = e[:, :scene.n_active]
+        dense = dense.cpu().numpy()
+        dense = dense.reshape((len(tf),) + tuple(pts_shape))
+        return dense[0] if np.ndim(t_frames) == 0 else dense
+
+    def save_params(self, directory, filename='NeRF_Predictor_params.yml'):
+        """network.py:239-247."""
+        import yaml
+        os.makedirs(directory, exist_ok=True)
+        keys = ['scale', 'rmin', 'rmax', 'z_width', 'posenc_deg', 'posenc_var', 'net_depth', 'net_width',
+                'out_channel', 'do_skip']
+        with open(os.path.join(directory, filename), 'w') as f:
+            yaml.dump({k: getattr(self, k) for k in keys}, f)
+
+    @classmethod
+    def from_yml(cls, directory, filename='NeRF_Predictor_params.yml'):
+        """network.py:249-252."""
+        import yaml
+        with open(os.path.join(directory, filename)) as f:
+            return cls(**yaml.safe_load(f))
+
+
+# ------------------------------------------------------------------------------------------------
+# scene cache: the 9 frame-independent raytracing args are prepacked once per (arrays, predictor)
+# ------------------------------------------------------------------------------------------------
+_scene_cache = OrderedDict()
+
+
+def _scene_for(predictor, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units, device=None):
+    tsv = float(utils.time_value(t_start_obs, t_units))
+    key = (id(coords), id(Omega), id(J) if not np.isscalar(J) else ('scalar', float(J)), id(g), id(dtau), id(Sigma),
+           id(t_geos), tsv, float(t_injection), predictor.scale, predictor.rmin, predictor.rmax, predictor.z_width,
+           str(t_units), str(device))
+    hit = _scene_cache.get(key)
+    if hit is not None:
+        _scene_cache.move_to_end(key)
+        return hit[0]
+    scene = engine.PackedScene(coords, Omega, J, g, dtau, Sigma, t_geos, tsv, float(t_injection), predictor.scale,
+                               predictor.rmin, predictor.rmax, predictor.z_width, constants.GM_c3(t_units=t_units),
+                               device=device)
+    # keep the source arrays alive so the id()-based key stays valid
+    _scene_cache[key] = (scene, (coords, Omega, J, g, dtau, Sigma, t_geos))
+    while len(_scene_cache) > 8:
+        _scene_cache.popitem(last=False)
+    return scene
+
+
+def _predictor_of(predictor_fn):
+    p = getattr(predictor_fn, '__self__', predictor_fn)
+    if not isinstance(p, NeRF_Predictor):
+        raise TypeError('predictor_fn must be NeRF_Predictor.apply (GRID_Predictor is out of scope, SURVEY s2 #8)')
+    return p
+
+
+def _flat(params, device):
+    if isinstance(params, torch.Tensor):
+        return params
+    return torch.as_tensor(flatten_params(params), device=device)
+
+
+def _shape_images(images, scene, J):
+    """(Bt,S,P) -> (Bt,A,B) for scalar J, (Bt,S,A,B) otherwise, then jnp.squeeze semantics of
+    network.py:418 (size-1 axes dropped when J is an array)."""
+    Bt = images.shape[0]
+    if not scene.polarized:
+        return images.reshape((Bt,) + scene.image_shape)
+    out = images.reshape((Bt, scene.S) + scene.image_shape)
+    return out.squeeze() if (Bt == 1 or scene.S == 1) else out
+
+
+def image_plane_prediction(params, predictor_fn, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos,
+                           t_injection, t_units, impl=None):
+    """bhnerf/network.py:373-420.  Returns a device tensor of images."""
+    pred = _predictor_of(predictor_fn)
+    scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units)
+    tf = np.atleast_1d(utils.time_value(t_frames, t_units)).astype(np.float32) if not isinstance(t_frames, torch.Tensor) else t_frames
+    images, _, _ = engine.render_fwd(scene, _flat(params, scene.device), tf, impl)
+    return _shape_images(images, scene, J)
+
+
+def _image_targets(scene, target, sigma, offset, dtype, Bt):
+    if dtype not in ('full', 'lc'):
+        raise AttributeError('image dtype ({}) not supported'.format(dtype))
+    return [engine._dev_f32(a, scene.device).reshape(Bt, -1) for a in (target, sigma, offset)]
+
+
+def loss_fn_image(params, predictor_fn, target, sigma, offset, t_frames, coords, Omega, J, g, dtau, Sigma,
+                  t_start_obs, t_geos, t_injection, scale, t_units, dtype, impl=None):
+    """bhnerf/network.py:422-484.  Returns (scale*loss, [images])."""
+    pred = _predictor_of(predictor_fn)
+    scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units)
+    tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
+                         scene.device).reshape(-1)
+    tgt, sig, off = _image_targets(scene, target, sigma, offset, dtype, tf.numel())
+    images, _, _ = engine.render_fwd(scene, _flat(params, scene.device), tf, impl)
+    loss, _ = engine.loss_image(images, tgt, sig, off, float(scale), dtype)
+    return loss, [_shape_images(images, scene, J)]
+
+
+def _eht_prepare(scene, target, sigma, A, dtype, Bt):
+    if dtype not in ('vis', 'amp', 'cphase'):
+        raise AttributeError('eht dtype ({}) not supported'.format(dtype))
+    if dtype == 'cphase':
+        raise NotImplementedError("eht dtype 'cphase' (closure phases, network.py:555-559) is not built yet")
+    if scene.S != 1:
+        raise NotImplementedError('polarized visibilities (A with a pol axis) are not built yet')
+    A = engine._c64(A, scene.device)
+    if A.dim() != 3 or A.shape[0] != Bt or A.shape[2] != scene.P:
+        raise AttributeError('A should have shape (nt, nvis, npix) = ({}, V, {}), got {}'.format(Bt, scene.P, tuple(A.shape)))
+    tshape = tuple(np.shape(target)) if not isinstance(target, torch.Tensor) else tuple(target.shape)
+    if len(tshape) != 2:
+        raise AttributeError('visibilities (ndim=2) should have same dimensions as target (ndim={}) for dtype={}'.format(len(tshape), dtype))
+    return A
+
+
+def loss_fn_eht(params, predictor_fn, target, sigma, A, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs,
+                t_geos, t_injection, scale, t_units, dtype, impl=None):
+    """bhnerf/network.py:486-564 ('vis' and 'amp')."""
+    pred = _predictor_of(predictor_fn)
+    scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units)
+    tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
+                         scene.device).reshape(-1)
+    A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
+    images, _, _ = engine.render_fwd(scene, _flat(params, scene.device), tf, impl)
+    vis = engine.vis_fwd(A, images)
+    loss, _ = engine.loss_vis(vis, target, sigma, float(scale), dtype)
+    return loss, [_shape_images(images, scene, J)]
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def _pmean_and_apply(state, grads, update=True):
+    """jax.lax.pmean(grads,'batch') + state.apply_gradients (network.py:620-621): all-reduce SUM over ranks,
+    the 1/ndev is folded into the Adam kernel's grad_scale."""
+    dist = _dist()
+    scale = 1.0
+    if dist is not None:
+        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+        scale = 1.0 / dist.get_world_size()
+    if update:
+        state.apply_gradients(grads, grad_scale=scale)
+    return state
+
+
+def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, coords, Omega, J, g, dtau, Sigma,
+                        t_start_obs, t_geos, t_injection, scale, impl=None):
+    """bhnerf/network.py:566-622: value_and_grad(loss_fn_image) -> pmean -> apply_gradients.
+    Returns (loss, state, images)."""
+    pred = state.predictor
+    scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units,
+                       device=state.flat.device)
+    tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
+                         scene.device).reshape(-1)
+    tgt, sig, off = _image_targets(scene, target, sigma, offset, dtype, tf.numel())
+    loss, images, grads = engine.train_step_image(scene, state.flat, tf, tgt, sig, off, float(scale), dtype, impl)
+    state = _pmean_and_apply(state, grads)
+    return loss, state, _shape_images(images, scene, J)
+
+
+def test_image(state, t_units, dtype, target, sigma, offset, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs,
+               t_geos, t_injection, scale, impl=None):
+    """bhnerf/network.py:684-739: forward + loss only."""
+    loss, [images] = loss_fn_image(state.flat, state.predictor.apply, target, sigma, offset, t_frames, coords, Omega,
+                                   J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, scale, t_units, dtype, impl)
+    return loss, state, images
+
+
+def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords, Omega, J, g, dtau, Sigma,
+                      t_start_obs, t_geos, t_injection, scale, impl=None):
+    """bhnerf/network.py:624-682."""
+    pred = state.predictor
+    scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units,
+                       device=state.flat.device)
+    tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
+                         scene.device).reshape(-1)
+    A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
+    images, e, acts = engine.render_fwd(scene, state.flat, tf, impl, save_acts=True)
+    vis = engine.vis_fwd(A, images)
+    loss, dvis = engine.loss_vis(vis, target, sigma, float(scale), dtype)
+    dI = engine.vis_bwd(A, dvis, scene.P)
+    grads = engine.render_bwd(scene, state.flat, tf, dI, e, acts, impl)
+    state = _pmean_and_apply(state, grads)
+    return loss, state, _shape_images(images, scene, J)
+
+
+def test_eht(state, t_units, dtype, target, sigma, A, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs,
+             t_geos, t_injection, scale, impl=None):
+    """bhnerf/network.py:741-795."""
+    loss, [images] = loss_fn_eht(state.flat, state.predictor.apply, target, sigma, A, t_frames, coords, Omega, J, g,
+                                 dtau, Sigma, t_start_obs, t_geos, t_injection, scale, t_units, dtype, impl)
+    return loss, state, images
+
+
+def raytracing_args(geos, Omega, t_injection, t_start_obs, J=1.0):
+    """bhnerf/network.py:850-894: ordered dict whose VALUE ORDER is the positional ABI of the step
+    functions.  ``geos`` is any mapping/namespace with x,y,z,t,dtau,Sigma and either ``g`` or the
+    fields kgeo.doppler_factor needs (r, theta, spin, M, E, lam, Xi)."""
+    from . import kgeo
+    get = (lambda k: geos[k]) if hasattr(geos, '__getitem__') else (lambda k: getattr(geos, k))
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    coords = f32([get('x'), get('y'), get('z')])
+    try:
+        gfac = get('g')
+    except (KeyError, AttributeError):
+        gfac = kgeo.doppler_factor(geos, kgeo.azimuthal_velocity_vector(geos, Omega))
+    return OrderedDict({
+        'coords': coords, 'Omega': f32(Omega), 'J': J if np.isscalar(J) else f32(J), 'g': f32(gfac),
+        'dtau': f32(get('dtau')), 'Sigma': f32(get('Sigma')), 't_start_obs': t_start_obs, 't_geos': f32(get('t')),
+        't_injection': t_injection})
+
+
+def sample_3d_grid(apply_fn, params, t_frame=0, t_start_obs=0, Omega=0, fov=None, coords=None, resolution=64,
+                   chunk=-1):
+    """bhnerf/network.py:797-840: emission on a res^3 grid with identity warp (t_geos=t_injection=0)."""
+    if (coords is None) and (fov is not None):
+        grid_1d = np.linspace(-fov / 2, fov / 2, resolution)
+        coords = np.array(np.meshgrid(grid_1d, grid_1d, grid_1d, indexing='ij'))
+    elif coords is None:
+        raise AttributeError('Either coords or fov+resolution must be provided')
+    t_units = getattr(t_frame, 'unit', None)
+    return apply_fn({'params': params}, t_frame, t_units, coords, Omega, t_start_obs, 0.0, 0.0)

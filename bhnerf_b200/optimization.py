@@ -1,0 +1,281 @@
+"""Mirror of the reference's ``bhnerf/optimization.py`` for the train-step orchestration.
+
+Data parallelism: the reference uses one process driving all GPUs with ``jax.pmap`` over observation
+frames and ``jax.lax.pmean`` of the gradients (optimization.py:209-216, network.py:620).  Here it is one
+process per GPU (``torch.distributed``, NCCL): ``shard`` gives each rank its contiguous slice of the
+batch's frames, every rank holds replicated geodesics + params, and the only exchange is the
+all-reduce(mean) of the 55 169-float gradient before Adam."""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from . import network, utils
+
+
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _same_on_all_ranks(values):
+    """The reference samples batch indices in its single driver process; with one process per GPU rank 0's
+    draw is broadcast so every rank works on the same batch."""
+    import torch.distributed as dist
+    if _world()[1] == 1:
+        return values
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    t = torch.as_tensor(np.asarray(values, dtype=np.int64), device=dev).clone()
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy().reshape(np.shape(values))
+
+
+def device_count():
+    """jax.device_count() analogue: number of ranks (one GPU each)."""
+    return _world()[1]
+
+
+def shard(xs):
+    """optimization.py:360-362 reshapes to (ndev, -1, ...) and pmap gives device d the d-th slice; here the
+    calling rank gets its slice directly.  The batch must divide evenly, as in the reference."""
+    rank, world = _world()
+
+    def one(x):
+        n = x.shape[0]
+        if n % world:
+            raise ValueError('batch of %d frames is not divisible by %d devices' % (n, world))
+        per = n // world
+        return x[rank * per:(rank + 1) * per]
+    if isinstance(xs, (list, tuple)):
+        return type(xs)(one(x) for x in xs)
+    return one(xs)
+
+
+def total_movie_loss(batchsize, state, train_step, raytracing_args, return_frames=False):
+    """optimization.py:14-66: chunk all frames, forward only, sum the loss / nt, optionally return frames.
+    With several ranks the per-rank losses are summed (the reference's ``loss.sum()`` over devices) and
+    the frames of every rank are gathered in order."""
+    nt = train_step.args[0].num_frames
+    ndev = device_count()
+    if nt % ndev:
+        raise AttributeError('batch size should be an integer multiplication of the device number')
+    nt_tilde = nt - nt % batchsize
+    indices = np.array_split(np.arange(0, nt_tilde), nt_tilde / batchsize) if nt_tilde else []
+    nt_tilde1 = int(ndev * np.ceil(nt / ndev))
+    indices.append(np.arange(nt_tilde, nt_tilde1) % nt)
+    frames, total_loss = [], 0.0
+    for inds in indices:
+        if inds.size == 0:
+            break
+        loss, state, images = train_step(state, raytracing_args, inds, update_state=False)
+        loss = _allreduce_scalar(loss)
+        total_loss += float(loss)
+        if return_frames:
+            images = _allgather_frames(images)
+            polarized = not np.isscalar(np.atleast_1d(raytracing_args)[0]['J'])
+            frames.append(images.reshape((-1,) + tuple(images.shape[-3:] if polarized else images.shape[-2:])))
+    output = total_loss / nt
+    if return_frames:
+        output = (output, np.concatenate([f.cpu().numpy() for f in frames])[:nt])
+    return output
+
+
+def _allreduce_scalar(loss):
+    import torch.distributed as dist
+    t = loss.detach().reshape(-1).sum().reshape(1).clone()
+    if _world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.item()
+
+
+def _allgather_frames(images):
+    import torch.distributed as dist
+    rank, world = _world()
+    if world == 1:
+        return images
+    outs = [torch.empty_like(images) for _ in range(world)]
+    dist.all_gather(outs, images.contiguous())
+    return torch.cat(outs, dim=0)
+
+
+class TemporalBatchedArgs(object):
+    """optimization.py:270-302."""
+
+    def __init__(self, t_frames, args=[]):
+        self.t_frames = t_frames
+        if not isinstance(args, list):
+            args = [args]
+        self.num_frames = len(t_frames)
+        assert all([self.num_frames == arg.shape[0] for arg in args])
+        self._t_values = np.asarray(utils.time_value(t_frames, 'hr'), dtype=np.float32)
+        args = list(args) + [self._t_values]
+        self.args = args
+        self.default_t_units = 'hr'
+
+    def sample(self, batchsize, replace=False):
+        return _same_on_all_ranks(np.random.choice(range(self.num_frames), batchsize, replace=replace))
+
+    def __getitem__(self, key):
+        return [shard(arg[key, ...]) for arg in self.args]
+
+    @property
+    def t_units(self):
+        unit = getattr(self.t_frames, 'unit', None)
+        return str(unit) if unit is not None else self.default_t_units
+
+    @property
+    def t_start_obs(self):
+        return self.t_frames[0]
+
+
+class TrainStep(object):
+    """optimization.py:145-268.  ``grad_pmap``/``test_pmap`` hold the step functions themselves (one rank =
+    one device; there is no pmap to build)."""
+
+    def __init__(self, dtype, args, grad_pmap, test_pmap, scale):
+        self.dtype = np.atleast_1d(dtype)
+        self.args = np.atleast_1d(args)
+        self.grad_pmap = np.atleast_1d(grad_pmap)
+        self.test_pmap = np.atleast_1d(test_pmap)
+        self.scale = np.atleast_1d(scale)
+        if np.any([arg.t_units not in ('hr', 'h') for arg in self.args]):
+            raise AttributeError('only hr units supported')
+        assert self.dtype.size == self.args.size == self.test_pmap.size == \
+            self.grad_pmap.size == self.scale.size, 'input list sizes are not equal'
+        self.num_losses = self.dtype.size
+
+    def __call__(self, state, raytracing_args, indices, update_state=True):
+        total_loss = 0.0
+        total_images = 0.0
+        raytracing_args = np.atleast_1d(raytracing_args)
+        if update_state:
+            call_fn = self.grad_pmap
+            raytracing_args = [raytracing_args[int(_same_on_all_ranks(np.random.choice(len(raytracing_args))))]]
+        else:
+            call_fn = self.test_pmap
+        for rt_arg in raytracing_args:
+            for i in range(self.num_losses):
+                loss, state, images = call_fn[i](state, self.t_units, self.dtype[i], *self.args[i][indices],
+                                                 *rt_arg.values(), self.scale[i])
+                total_loss = total_loss + loss / len(raytracing_args)
+                total_images = total_images + images / len(raytracing_args)
+        return total_loss, state, total_images
+
+    def __add__(self, other):
+        return TrainStep(np.append(self.dtype, other.dtype), np.append(self.args, other.args),
+                         np.append(self.grad_pmap, other.grad_pmap), np.append(self.test_pmap, other.test_pmap),
+                         np.append(self.scale, other.scale))
+
+    @classmethod
+    def image(cls, t_frames, target, sigma=1.0, offset=0.0, scale=1.0, dtype='full'):
+        """optimization.py:189-216."""
+        target = np.asarray(target, dtype=np.float32)
+        sigma = (sigma * np.ones_like(target)).astype(np.float32)
+        offset = (offset * np.ones_like(target)).astype(np.float32)
+        args = TemporalBatchedArgs(t_frames, [target, sigma, offset])
+        return cls(dtype, args, network.gradient_step_image, network.test_image, scale)
+
+    @classmethod
+    def eht(cls, t_frames, target, sigma, A, dtype='vis', scale=1.0):
+        """optimization.py:218-268 minus the ehtim calls: the reference builds (target, sigma, A) with
+        ``ehtim.imaging.imager_utils.chisqdata_<dtype>`` (third party, absent here); they are inputs of
+        the hot path, so this constructor takes them directly.  A: (nt, nvis, npix) complex64."""
+        target = np.asarray(target)
+        args = TemporalBatchedArgs(t_frames, [target, np.asarray(sigma, dtype=np.float32),
+                                              np.asarray(A, dtype=np.complex64)])
+        return cls(dtype, args, network.gradient_step_eht, network.test_eht, scale)
+
+    @property
+    def t_units(self):
+        return self.args[0].t_units
+
+
+def save_checkpoint(checkpoint_dir, state, step, keep=5):
+    """Stand-in for flax.training.checkpoints.save_checkpoint (optimization.py:118-121): same file naming
+    (``checkpoint_<step>``) and ``keep`` policy; payload is a pickled dict of numpy arrays with the flax
+    tree names (msgpack/flax are not installed)."""
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    with open(os.path.join(checkpoint_dir, 'checkpoint_%d' % step), 'wb') as f:
+        pickle.dump(state.state_dict(), f)
+    ck = sorted([int(n.split('_')[1]) for n in os.listdir(checkpoint_dir) if n.startswith('checkpoint_')])
+    for s in ck[:-keep]:
+        os.remove(os.path.join(checkpoint_dir, 'checkpoint_%d' % s))
+
+
+def restore_checkpoint(checkpoint_dir, state):
+    if not os.path.isdir(checkpoint_dir):
+        return state
+    ck = sorted([int(n.split('_')[1]) for n in os.listdir(checkpoint_dir) if n.startswith('checkpoint_')])
+    if not ck:
+        return state
+    with open(os.path.join(checkpoint_dir, 'checkpoint_%d' % ck[-1]), 'rb') as f:
+        d = pickle.load(f)
+    dev = state.flat.device
+    state.flat.copy_(torch.as_tensor(network.flatten_params(d['params']), device=dev))
+    state.mu.copy_(torch.as_tensor(d['mu'], device=dev)); state.nu.copy_(torch.as_tensor(d['nu'], device=dev))
+    state.step = int(d['step'])
+    return state
+
+
+class Optimizer(object):
+    """optimization.py:68-143."""
+
+    def __init__(self, hparams, predictor, raytracing_args, save_period=-1, checkpoint_dir='', keep=5):
+        self.step = 0
+        self.init_step = 0
+        self.num_iters = hparams['num_iters']
+        self.checkpoint_dir = checkpoint_dir
+        self.save_period = self.num_iters if save_period < 0 else save_period
+        self.loss = np.inf
+        self.keep = keep
+        self.seed = hparams.get('seed', 1)
+        params = predictor.init_params(raytracing_args, seed=self.seed)
+        self.state = predictor.init_state(params=params, num_iters=self.num_iters,
+                                          lr_init=hparams.get('lr_init', 1e-4), lr_final=hparams.get('lr_final', 1e-6),
+                                          lr_inject=hparams.get('lr_inject', None), checkpoint_dir=self.checkpoint_dir)
+        if checkpoint_dir != '':
+            predictor.save_params(checkpoint_dir)
+
+    def log(self):
+        for log_fn in self.log_fns:
+            log_fn(self)
+
+    def save_checkpoint(self):
+        if (self.checkpoint_dir != '') and ((self.step % self.save_period == 0) or (self.step == self.final_step)):
+            if _world()[0] == 0:
+                save_checkpoint(self.checkpoint_dir, self.state, int(self.step), keep=self.keep)
+
+    def run(self, batchsize, train_step, raytracing_args, log_fns=[]):
+        self.init_step = self.state.step + 1
+        self.final_step = self.init_step + self.num_iters
+        self.log_fns = np.atleast_1d(log_fns)
+        self.train_step = train_step
+        self.raytracing_args = raytracing_args
+        try:
+            for self.step in range(self.init_step, self.final_step):
+                batch_indices = train_step.args[0].sample(batchsize)
+                self.loss, self.state, images = train_step(self.state, raytracing_args, indices=batch_indices)
+                self.log()
+                self.save_checkpoint()
+        except KeyboardInterrupt:
+            return
+
+    @property
+    def params(self):
+        return self.state.params
+
+
+class LogFn(object):
+    """optimization.py:349-357."""
+
+    def __init__(self, log_fn, log_period=1):
+        self.log_period = log_period
+        self.log_fn = log_fn
+
+    def __call__(self, optimizer):
+        if self.log_period > 0:
+            if (optimizer.step == 1) or ((optimizer.step % self.log_period) == 0):
+                self.log_fn(optimizer)

@@ -1,0 +1,151 @@
+/* bhnerf_b200 -- C ABI of the B200-native bhnerf render/train hot path.
+ *
+ * The reference (aviadlevis/bhnerf) has no native FFI for this path: the seam is its Python API
+ * (SURVEY.md s8b).  Each entry point below names the reference function it replaces
+ * (paths under the reference repo).  A JAX binding registers these through jax.ffi
+ * (see INTEGRATION.md); the ctypes host in bhnerf_b200/_lib.py binds them directly.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; arrays are row-major fp32
+ *     unless noted; complex64 is interleaved (re,im) fp32
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns;
+ *     the only exception is bhnerf_prepack (one stream sync to return n_active)
+ *   - no allocation on the call path: scratch comes from the caller-provided workspace
+ *   - return value: 0 = ok, non-zero = error (message via bhnerf_last_error, thread-local)
+ *   - no CPU fallback exists: on a machine without an sm_100 GPU the calls fail with an error
+ */
+#ifndef BHNERF_B200_H
+#define BHNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BHNERF_ABI_VERSION 1
+#define BHNERF_N_PARAMS 55169      /* 21x128+128, 128x128+128 (x2), 149x128+128, 128x1+1 */
+#define BHNERF_N_FEAT 21
+#define BHNERF_WIDTH 128
+
+/* which kernel family runs the MLP */
+#define BHNERF_IMPL_SIMT 0         /* fp32 FFMA reference kernels (CUDA cores)              */
+#define BHNERF_IMPL_TC   1         /* tcgen05 tensor cores, bf16x3 split operands, fp32 acc */
+
+/* loss kinds: bhnerf/network.py:476-484 ('full','lc') and :542-564 ('vis','amp','cphase') */
+#define BHNERF_LOSS_FULL 0
+#define BHNERF_LOSS_LC   1
+#define BHNERF_LOSS_VIS  2
+#define BHNERF_LOSS_AMP  3
+#define BHNERF_LOSS_CPHASE 4
+
+/* A prepacked scene = the frame-independent part of network.raytracing_args
+ * (bhnerf/network.py:850-894) + the NeRF_Predictor constants (bhnerf/network.py:147-157).
+ * Filled by bhnerf_prepack; plain data, may be copied freely. */
+typedef struct bhnerf_scene {
+  const void* packed;     /* device buffer written by bhnerf_prepack                       */
+  int32_t n_active;       /* samples inside the recovery domain with non-zero weight       */
+  int32_t n_pad;          /* n_active rounded up to a multiple of 128 (padding has w = 0)  */
+  int32_t P;              /* rays = num_alpha*num_beta                                     */
+  int32_t G;              /* samples per ray (ngeo)                                        */
+  int32_t S;              /* Stokes channels: 1 when J is the scalar 1.0, else J.shape[0]  */
+  float t_start_obs;      /* [t_units]  raytracing_args['t_start_obs']                     */
+  float GM_c3;            /* GM/c^3 in t_units (emission.py:183-185)                       */
+  float t_injection;      /* [M]                                                           */
+  float scale;            /* NeRF_Predictor.scale (network.py:229)                         */
+} bhnerf_scene_t;
+
+const char* bhnerf_last_error(void);
+int bhnerf_version(void);
+/* number of SMs / compute capability of the current device; fails if it is not sm_100 */
+int bhnerf_device_check(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ---- setup: replaces the per-call masking of emission.fill_unsupervised_emission
+ * (bhnerf/emission.py:343-374, applied at network.py:231) and folds
+ * w_s = g^2 * dtau * Sigma * J_s (kgeo.radiative_trasfer, bhnerf/kgeo.py:618-621; J broadcast
+ * network.py:415-418).  The domain mask uses UN-warped coords so it is frame independent.
+ * coords [3,P,G]; Omega,g,dtau,Sigma,t_geos [P,G]; J [S,P,G] or NULL (scalar 1.0).          */
+size_t bhnerf_packed_bytes(int32_t P, int32_t G, int32_t S);   /* upper bound (all active)   */
+int bhnerf_prepack(const float* coords, const float* Omega, const float* g, const float* dtau,
+                   const float* Sigma, const float* t_geos, const float* J,
+                   int32_t P, int32_t G, int32_t S, float rmin, float rmax, float z_width,
+                   void* packed, size_t packed_bytes, bhnerf_scene_t* scene_host, void* stream);
+
+/* ---- forward render: replaces network.image_plane_prediction (bhnerf/network.py:373-420) =
+ * NeRF_Predictor.__call__ (:191-237: velocity_warp_coords emission.py:143-211, posenc :98-122,
+ * MLP :18-64, sigmoid(o-10) :230, masks :231-232) + kgeo.radiative_trasfer (kgeo.py:595-622).
+ * images [Bt,S,P] (overwritten).  e_out [Bt,n_pad] (required): per-sample masked emission, the
+ * residual the backward needs.  acts_out or NULL: saved activations for the backward
+ * (bhnerf_acts_bytes(scene,Bt,impl) bytes; bf16 tiles for TC, fp32 rows for SIMT).           */
+size_t bhnerf_acts_bytes(const bhnerf_scene_t* scene, int32_t Bt, int32_t impl);
+size_t bhnerf_fwd_workspace_bytes(int32_t impl);   /* bf16 weight images of the TC family; 0 for SIMT */
+int bhnerf_render_fwd(const bhnerf_scene_t* scene, const float* params, const float* t_frames,
+                      int32_t Bt, float* images, float* e_out, void* acts_out, void* workspace,
+                      size_t workspace_bytes, int32_t impl, void* stream);
+
+/* ---- backward render: replaces the jax.value_and_grad pull-back through
+ * image_plane_prediction (bhnerf/network.py:617, :677), gradient w.r.t. params only.
+ * d_params [55169] is OVERWRITTEN.  e_saved/acts_saved from the matching forward, or NULL:
+ * the backward then recomputes them frame-chunk by frame-chunk inside `workspace`
+ * (>= bhnerf_bwd_workspace_bytes).                                                           */
+size_t bhnerf_bwd_workspace_bytes(const bhnerf_scene_t* scene, int32_t Bt, int32_t impl);
+int bhnerf_render_bwd(const bhnerf_scene_t* scene, const float* params, const float* t_frames,
+                      int32_t Bt, const float* d_images, const float* e_saved,
+                      const void* acts_saved, float* d_params, void* workspace,
+                      size_t workspace_bytes, int32_t impl, void* stream);
+
+/* ---- loss heads (value + d_images in one pass)
+ * image: loss_fn_image (bhnerf/network.py:422-484). target/sigma/offset are [Bt,S,P] ('full')
+ * or [Bt,S] ('lc').  loss[1] overwritten; d_images [Bt,S,P] overwritten.                     */
+int bhnerf_loss_image(const float* images, const float* target, const float* sigma,
+                      const float* offset, float loss_scale, int32_t kind, int32_t Bt, int32_t S,
+                      int32_t P, float* loss, float* d_images, void* stream);
+/* eht: loss_fn_eht (bhnerf/network.py:486-564).  A [Bt,V,P] complex64 (one DFT matrix per
+ * frame), images [Bt,P] (S must be 1), target [Bt,V] complex64 ('vis') or fp32 ('amp'),
+ * sigma [Bt,V].  vis [Bt,V] complex64 overwritten.                                           */
+int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, int32_t V, int32_t P,
+                   float* vis, void* stream);
+int bhnerf_loss_vis(const float* vis, const float* target, const float* sigma, float loss_scale,
+                    int32_t kind, int32_t Bt, int32_t V, float* loss, float* d_vis, void* stream);
+int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, int32_t V, int32_t P,
+                   float* d_images, void* stream);
+
+/* ---- fused train step for the separable image losses: per frame chunk
+ * fwd -> ray integral -> loss -> bwd with activations kept in `workspace`.  Replaces
+ * gradient_step_image up to (not including) pmean/apply_gradients (network.py:617-619).
+ * images [Bt,S,P], loss[1], d_params[55169] overwritten.                                     */
+size_t bhnerf_train_workspace_bytes(const bhnerf_scene_t* scene, int32_t Bt, int32_t impl);
+int bhnerf_train_step_image(const bhnerf_scene_t* scene, const float* params,
+                            const float* t_frames, int32_t Bt, const float* target,
+                            const float* sigma, const float* offset, float loss_scale,
+                            int32_t kind, float* loss, float* images, float* d_params,
+                            void* workspace, size_t workspace_bytes, int32_t impl, void* stream);
+
+/* ---- stand-alone dense stages with the reference's public names (fused inside render_*).
+ * velocity_warp_coords: emission.velocity_warp_coords (bhnerf/emission.py:143-211), rot_axis = z.
+ *   coords [3,N], Omega/t_geos [N], out [Bt,N,3]; NaN where t_M < 0 (emission.py:205).
+ * fill_unsupervised_emission: bhnerf/emission.py:343-374, in place on emission [R,N], coords [3,N].
+ * radiative_transfer: kgeo.radiative_trasfer (bhnerf/kgeo.py:595-622), emission [R,P,G] -> out [R,P]. */
+int bhnerf_velocity_warp_coords(const float* coords, const float* Omega, const float* t_geos,
+                                int64_t N, const float* t_frames, int32_t Bt, float t_start_obs,
+                                float GM_c3, float t_injection, float* out, void* stream);
+int bhnerf_fill_unsupervised_emission(float* emission, const float* coords, int32_t R, int64_t N,
+                                      float rmin, float rmax, float z_width, float fill_value,
+                                      void* stream);
+int bhnerf_radiative_transfer(const float* emission, const float* g, const float* dtau,
+                              const float* Sigma, int32_t R, int32_t P, int32_t G, float* out,
+                              void* stream);
+
+/* ---- optimiser: optax.adam + polynomial_schedule(power=1) applied by
+ * TrainState.apply_gradients (bhnerf/network.py:171-182, :621).  grad_scale multiplies the
+ * gradient first (1/ndev turns an all-reduce SUM into jax.lax.pmean, network.py:620).
+ * count = number of updates already applied.                                                 */
+int bhnerf_adam_step(float* params, const float* grads, float* mu, float* nu, int32_t n,
+                     int32_t count, float lr_init, float lr_final, int32_t transition_steps,
+                     float b1, float b2, float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHNERF_B200_H */

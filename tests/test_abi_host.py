@@ -1,0 +1,130 @@
+"""CPU tests: the C-ABI library builds, loads and exports every symbol the header declares; host logic
+(parameter packing, frame sharding over 2 gloo ranks, schedule, API error behaviour)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol(built_lib):
+    from bhnerf_b200 import _lib
+    declared = _lib.header_functions()
+    assert len(declared) >= 20
+    assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert built_lib.bhnerf_version() == 1
+    # nm view: every declared function is an exported text symbol
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert (' T ' + name) in out, name
+
+
+def test_library_contains_sm100a_code(built_lib):
+    from bhnerf_b200 import _lib
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from bhnerf_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(_lib.BhnerfError, match='no CPU fallback'):
+        _lib.load()
+
+
+def test_param_packing_matches_oracle_layout():
+    from bhnerf_b200 import network
+    from oracle import bhnerf_oracle as O
+    p = O.trained_like_params(5)
+    np.testing.assert_array_equal(network.flatten_params(p), O.flatten_params(p))
+    q = network.unflatten_params(network.flatten_params(p))
+    np.testing.assert_array_equal(q['MLP_0']['Dense_3']['kernel'], p['MLP_0']['Dense_3']['kernel'])
+    bad = {'MLP_0': dict(p['MLP_0'])}
+    bad['MLP_0']['Dense_3'] = {'kernel': np.zeros((128, 128), np.float32), 'bias': np.zeros(128, np.float32)}
+    with pytest.raises(ValueError):
+        network.flatten_params(bad)
+
+
+def test_predictor_rejects_unsupported_architectures():
+    from bhnerf_b200 import network
+    network.NeRF_Predictor(8.0, 2.0, 8.0, 4.0)
+    with pytest.raises(NotImplementedError):
+        network.NeRF_Predictor(net_width=256)
+    with pytest.raises(NotImplementedError):
+        network.NeRF_Predictor(posenc_deg=4)
+
+
+def test_constants_match_oracle():
+    from bhnerf_b200 import constants
+    from oracle import bhnerf_oracle as O
+    assert abs(constants.GM_c3(t_units='hr') - O.GM_C3_SGRA_HR) < 1e-18
+    assert abs(constants.GM_c3(t_units='hr') - 5.68347e-3) < 1e-8
+    assert abs(constants.isco_pro(0.0) - 6.0) < 1e-12
+
+
+def test_temporal_batched_args_and_trainstep_single_rank():
+    from bhnerf_b200 import optimization as opt
+    t = np.linspace(0, 1, 12)
+    tgt = np.arange(12 * 4, dtype=np.float32).reshape(12, 4)
+    ts = opt.TrainStep.image(t, tgt, sigma=0.5, dtype='lc')
+    a = ts.args[0]
+    assert a.num_frames == 12 and a.t_units == 'hr'
+    target, sigma, offset, tf = a[np.array([3, 7])]
+    np.testing.assert_array_equal(target, tgt[[3, 7]])
+    assert (sigma == 0.5).all() and (offset == 0).all()
+    np.testing.assert_allclose(tf, t[[3, 7]].astype(np.float32))
+    idx = a.sample(6)
+    assert len(set(idx.tolist())) == 6 and idx.max() < 12
+    both = ts + opt.TrainStep.image(t, tgt, dtype='full')
+    assert both.num_losses == 2 and list(both.dtype) == ['lc', 'full']
+
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from bhnerf_b200 import optimization as opt, network
+dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=2)
+rank = dist.get_rank()
+t = np.linspace(0, 1, 8); tgt = np.arange(8 * 3, dtype=np.float32).reshape(8, 3)
+a = opt.TemporalBatchedArgs(t, [tgt])
+np.random.seed(100 + rank)                       # different draws per rank ...
+idx = a.sample(4)                                # ... but rank 0's draw is used everywhere
+gathered = [None, None]; dist.all_gather_object(gathered, idx.tolist())
+assert gathered[0] == gathered[1], gathered
+target, tf = a[idx]
+assert target.shape == (2, 3)                    # 4 frames / 2 ranks (optimization.py:360-362)
+np.testing.assert_array_equal(target, tgt[idx][rank * 2:(rank + 1) * 2])
+# pmean: all-reduce SUM then 1/ndev (network.py:620)
+g = torch.full((5,), float(rank + 1))
+class S:                                          # minimal state stub (no GPU on this box)
+    def apply_gradients(self, grads, grad_scale=1.0): self.g = grads * grad_scale; return self
+s = network._pmean_and_apply(S(), g)
+assert torch.allclose(s.g, torch.full((5,), 1.5)), s.g
+try:
+    opt.shard(np.zeros((3, 2)))
+    raise SystemExit('shard should reject 3 frames on 2 ranks')
+except ValueError:
+    pass
+assert opt.device_count() == 2
+loss = opt._allreduce_scalar(torch.tensor([float(rank + 1)]))
+assert loss == 3.0
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_frame_sharding_and_pmean_two_gloo_ranks(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER % {'root': ROOT})
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29531', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

@@ -46,6 +46,9 @@ SIGNATURES = {
     'bhnerf_velocity_warp_coords': (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _i32, _f32, _f32, _f32, _vp, _vp]),
     'bhnerf_fill_unsupervised_emission': (C.c_int, [_vp, _vp, _i32, C.c_int64, _f32, _f32, _f32, _f32, _vp]),
     'bhnerf_radiative_transfer': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    'bhnerf_launch_count': (C.c_int64, []),
+    'bhnerf_profile_begin': (C.c_int, []),
+    'bhnerf_profile_end': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'bhnerf_adam_step': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _i32, _f32, _f32, _f32, _f32,
                                    _vp]),
 }

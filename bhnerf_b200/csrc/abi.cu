@@ -22,6 +22,66 @@ extern "C" int bhnerf_device_check(int* sm_count, int* cc_major, int* cc_minor) 
   return 0;
 }
 
+// ---- launch accounting / event timing ----
+#include <mutex>
+#include <vector>
+static std::mutex g_prof_mu;
+static unsigned long long g_launches[BH_NCAT] = {0, 0, 0, 0, 0};
+static bool g_prof_on = false;
+struct ProfRec { int cat; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void bh_prof_begin(int cat, int n_launches, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_launches[cat] += (unsigned long long)n_launches;
+  if (!g_prof_on) return;
+  ProfRec r; r.cat = cat; r.a = prof_event(); r.b = prof_event();
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+}
+void bh_prof_end(int cat, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on || g_prof_recs.empty()) return;
+  for (size_t i = g_prof_recs.size(); i-- > 0;)
+    if (g_prof_recs[i].cat == cat) { cudaEventRecord(g_prof_recs[i].b, st); break; }
+}
+extern "C" int bhnerf_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+  g_prof_recs.clear();
+  for (int c = 0; c < BH_NCAT; ++c) g_launches[c] = 0;
+  g_prof_on = true;
+  return 0;
+}
+// ms[5], scopes[5] (timed launch groups), launches[5] (kernels launched) per category since profile_begin
+extern "C" int bhnerf_profile_end(double* ms_host, int64_t* scopes_host, int64_t* launches_host) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  BH_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < BH_NCAT; ++c) { if (ms_host) ms_host[c] = 0.0; if (scopes_host) scopes_host[c] = 0; }
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (ms_host) ms_host[r.cat] += ms;
+      if (scopes_host) scopes_host[r.cat] += 1;
+    }
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+  if (launches_host) for (int c = 0; c < BH_NCAT; ++c) launches_host[c] = (int64_t)g_launches[c];
+  g_prof_on = false;
+  return 0;
+}
+extern "C" int64_t bhnerf_launch_count(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  unsigned long long t = 0;
+  for (int c = 0; c < BH_NCAT; ++c) t += g_launches[c];
+  return (int64_t)t;
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static FrameConsts frame_consts(const bhnerf_scene_t* sc) {
   FrameConsts fc; fc.t_start_obs = sc->t_start_obs; fc.GM_c3 = sc->GM_c3; fc.t_injection = sc->t_injection;

@@ -38,6 +38,16 @@ void bh_set_error(const char* fmt, ...);
     if (!(cond)) { bh_set_error(__VA_ARGS__); return 1; }                           \
   } while (0)
 
+// ---- launch accounting + optional per-category CUDA-event timing (bench.py's live roofline) ----
+enum { BH_CAT_FWD = 0, BH_CAT_BWD = 1, BH_CAT_WGRAD = 2, BH_CAT_HEADS = 3, BH_CAT_MISC = 4, BH_NCAT = 5 };
+void bh_prof_begin(int cat, int n_launches, cudaStream_t st);
+void bh_prof_end(int cat, cudaStream_t st);
+struct BhProfScope {
+  int cat; cudaStream_t st;
+  BhProfScope(int c, int n, cudaStream_t s) : cat(c), st(s) { bh_prof_begin(c, n, s); }
+  ~BhProfScope() { bh_prof_end(cat, st); }
+};
+
 // ---- packed scene view ----
 // buffer layout: row_ptr[int32 rp_pad] | x | y | z | omega | tgeo | w[S] | ray[int32] | kidx[int32]  (each n_pad)
 struct PackedView {

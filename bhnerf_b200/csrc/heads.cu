@@ -21,6 +21,7 @@ __global__ void ray_integrate_kernel(PackedView v, const float* __restrict__ e, 
 }
 
 int bh_launch_ray_integrate(const PackedView& v, const float* e, int Bt, float* images, cudaStream_t st) {
+  BhProfScope ps(BH_CAT_HEADS, 1, st);
   dim3 grid((v.P + 127) / 128, Bt);
   ray_integrate_kernel<<<grid, 128, 0, st>>>(v, e, Bt, images);
   BH_CHECK_CUDA(cudaGetLastError());
@@ -84,6 +85,7 @@ __global__ void loss_lc_kernel(const float* __restrict__ I, const float* __restr
 int bh_loss_image_accum(const float* images, const float* target, const float* sigma, const float* offset,
                         float loss_scale, int kind, int Bt, int S, int P, float* loss, float* d_images,
                         cudaStream_t st) {
+  BhProfScope ps(BH_CAT_HEADS, 1, st);
   if (kind == BHNERF_LOSS_FULL) {
     size_t n = (size_t)Bt * S * P;
     int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
@@ -185,6 +187,7 @@ __global__ void loss_vis_kernel(const float2* __restrict__ vis, const float* __r
 extern "C" int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, int32_t V, int32_t P, float* vis,
                               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  BhProfScope ps(BH_CAT_HEADS, 1, st);
   dim3 grid((V * 32 + 255) / 256, Bt);
   vis_fwd_kernel<<<grid, 256, 0, st>>>((const float2*)A, images, V, P, (float2*)vis);
   BH_CHECK_CUDA(cudaGetLastError());
@@ -198,6 +201,7 @@ extern "C" int bhnerf_loss_vis(const float* vis, const float* target, const floa
   BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   int n = Bt * V;
   int blocks = (n + 255) / 256; if (blocks > 592) blocks = 592;
+  BhProfScope ps(BH_CAT_HEADS, 1, st);
   loss_vis_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, kind, n, loss,
                                           (float2*)d_vis);
   BH_CHECK_CUDA(cudaGetLastError());
@@ -208,6 +212,7 @@ extern "C" int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, in
                               float* d_images, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BH_REQUIRE((size_t)V * sizeof(float2) <= 48 * 1024, "vis_bwd: V=%d too large", V);
+  BhProfScope ps(BH_CAT_HEADS, 1, st);
   dim3 grid((P + 255) / 256, Bt);
   vis_bwd_kernel<<<grid, 256, V * sizeof(float2), st>>>((const float2*)A, (const float2*)d_vis, V, P, d_images);
   BH_CHECK_CUDA(cudaGetLastError());
@@ -240,6 +245,7 @@ extern "C" int bhnerf_adam_step(float* params, const float* grads, float* mu, fl
   float lr = (float)((double)(lr_init - lr_final) * frac + (double)lr_final);
   double t = (double)count + 1.0;
   float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
+  BhProfScope ps(BH_CAT_MISC, 1, st);
   adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(params, grads, mu, nu, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -271,6 +277,7 @@ extern "C" int bhnerf_velocity_warp_coords(const float* coords, const float* Ome
   BH_REQUIRE(coords && Omega && t_geos && t_frames && out && N > 0 && Bt > 0 && GM_c3 > 0.f, "velocity_warp_coords: bad argument");
   FrameConsts fc; fc.t_start_obs = t_start_obs; fc.GM_c3 = GM_c3; fc.t_injection = t_injection; fc.scale = 1.f;
   dim3 grid((unsigned)((N + 255) / 256), Bt);
+  BhProfScope ps(BH_CAT_MISC, 1, (cudaStream_t)stream);
   warp_coords_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(coords, Omega, t_geos, (size_t)N, t_frames, fc, out);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -290,6 +297,7 @@ extern "C" int bhnerf_fill_unsupervised_emission(float* emission, const float* c
                                                  void* stream) {
   BH_REQUIRE(emission && coords && R > 0 && N > 0, "fill_unsupervised_emission: bad argument");
   dim3 grid((unsigned)((N + 255) / 256), R);
+  BhProfScope ps(BH_CAT_MISC, 1, (cudaStream_t)stream);
   fill_unsupervised_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(emission, coords, (size_t)N, rmin * rmin,
                                                                    rmax * rmax, z_width, fill_value);
   BH_CHECK_CUDA(cudaGetLastError());
@@ -315,6 +323,7 @@ extern "C" int bhnerf_radiative_transfer(const float* emission, const float* g, 
                                          int32_t R, int32_t P, int32_t G, float* out, void* stream) {
   BH_REQUIRE(emission && g && dtau && Sigma && out && R > 0 && P > 0 && G > 0, "radiative_transfer: bad argument");
   dim3 grid((P * 32 + 255) / 256, R);
+  BhProfScope ps(BH_CAT_MISC, 1, (cudaStream_t)stream);
   radiative_transfer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(emission, g, dtau, Sigma, P, G, out);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;

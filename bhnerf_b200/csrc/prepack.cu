@@ -132,6 +132,7 @@ extern "C" int bhnerf_prepack(const float* coords, const float* Omega, const flo
   int32_t* rp = (int32_t*)packed;
   float rmin2 = rmin * rmin, rmax2 = rmax * rmax;
   int threads = 256, blocks = (P * 32 + threads - 1) / threads;
+  bh_prof_begin(BH_CAT_MISC, 4, st); bh_prof_end(BH_CAT_MISC, st);
   prepack_count_kernel<<<blocks, threads, 0, st>>>(coords, g, dtau, Sigma, P, G, rmin2, rmax2, z_width, rp);
   prepack_scan_kernel<<<1, 1024, 0, st>>>(rp, P);
   int32_t n_active = 0;

@@ -86,6 +86,7 @@ simt_fwd_kernel(PackedView v, FrameConsts fc, const float* __restrict__ params,
 
 int bh_simt_fwd(const PackedView& v, const FrameConsts& fc, const float* params, const float* t_frames, int Bt,
                 float* e_out, float* acts, cudaStream_t st) {
+  BhProfScope ps(BH_CAT_FWD, 1, st);
   dim3 grid(v.n_pad / 128, Bt);
   if (acts) {
     BH_CHECK_CUDA(cudaFuncSetAttribute(simt_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -243,15 +244,17 @@ simt_wgrad_kernel(const float* __restrict__ A, int KA, const float* __restrict__
 
 int bh_simt_bwd(const PackedView& v, const float* params, const float* d_images, int Bt, const float* e_saved,
                 const float* acts, float* delta_ws, float* wt_ws, float* d_params, cudaStream_t st) {
-  simt_transpose_w_kernel<<<dim3(64, 3), 256, 0, st>>>(params, wt_ws);
+  { BhProfScope ps(BH_CAT_MISC, 1, st); simt_transpose_w_kernel<<<dim3(64, 3), 256, 0, st>>>(params, wt_ws); }
   size_t smem = (2 * 128 * PITCH + 128) * sizeof(float);
   BH_CHECK_CUDA(cudaFuncSetAttribute(simt_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(v.n_pad / 128, Bt);
-  simt_chain_kernel<<<grid, 128, smem, st>>>(v, params, wt_ws, d_images, e_saved, acts, delta_ws, d_params);
+  { BhProfScope ps(BH_CAT_BWD, 1, st);
+    simt_chain_kernel<<<grid, 128, smem, st>>>(v, params, wt_ws, d_images, e_saved, acts, delta_ws, d_params); }
   size_t np = (size_t)v.n_pad;
   size_t afs = bh_simt_acts_floats_per_frame(v.n_pad), dfs = bh_simt_delta_floats_per_frame(v.n_pad);
   dim3 wg((v.n_pad + WG_CHUNK - 1) / WG_CHUNK, Bt);
   const float* feat = acts + 4 * 128 * np;
+  BhProfScope ps(BH_CAT_WGRAD, 5, st);
   // layer 0: in = feat (21 rows);  layers 1,2: in = h_{l-1};  layer 3: in = [h2 | feat] (network.py:61)
   simt_wgrad_kernel<<<wg, 256, 0, st>>>(feat, BH_NF, delta_ws + 0 * 128 * np, v.n_pad, afs, dfs, d_params + OFF_W0);
   simt_wgrad_kernel<<<wg, 256, 0, st>>>(acts + 0 * 128 * np, 128, delta_ws + 1 * 128 * np, v.n_pad, afs, dfs, d_params + OFF_W1);

@@ -27,6 +27,8 @@ def resolve_impl(impl=None):
 
 
 DEFAULT_IMPL = IMPL_SIMT   # switched to IMPL_TC once the tcgen05 family is parity-green on hardware
+# cap on the activation workspace of one fused step / backward; more frames than fit are processed in chunks
+DEFAULT_MAX_WORKSPACE = int(float(os.environ.get('BHNERF_MAX_WORKSPACE_GB', '16')) * 2 ** 30)
 
 
 def _ptr(t):
@@ -159,7 +161,8 @@ def render_bwd(scene, params, t_frames, d_images, e=None, acts=None, impl=None, 
     assert d_images.numel() == Bt * scene.S * scene.P
     one = lib.bhnerf_bwd_workspace_bytes(scene.ref, Bt, impl)
     full = one + (one - 1024) * (Bt - 1)
-    nbytes = full if max_workspace is None else max(one, min(full, int(max_workspace)))
+    max_workspace = DEFAULT_MAX_WORKSPACE if max_workspace is None else max_workspace
+    nbytes = max(one, min(full, int(max_workspace)))
     ws = workspace(nbytes, dev)
     grads = torch.empty(N_PARAMS, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -239,7 +242,8 @@ def train_step_image(scene, params, t_frames, target, sigma, offset, scale, kind
     assert target.numel() == want and sigma.numel() == want and offset.numel() == want, 'target shape mismatch'
     full = lib.bhnerf_train_workspace_bytes(scene.ref, Bt, impl)
     one = lib.bhnerf_train_workspace_bytes(scene.ref, 1, impl)
-    nbytes = full if max_workspace is None else max(one, min(full, int(max_workspace)))
+    max_workspace = DEFAULT_MAX_WORKSPACE if max_workspace is None else max_workspace
+    nbytes = max(one, min(full, int(max_workspace)))
     ws = workspace(nbytes, dev)
     if out is None:
         out = (torch.empty(1, dtype=torch.float32, device=dev),
@@ -251,6 +255,14 @@ def train_step_image(scene, params, t_frames, target, sigma, offset, scale, kind
                                           _ptr(offset), float(scale), k, _ptr(loss), _ptr(images), _ptr(grads),
                                           _ptr(ws), nbytes, impl, _stream()))
     return loss, images, grads
+
+
+def frames_per_chunk(scene, Bt, impl=None, max_workspace=None):
+    """How many frames of saved activations fit the workspace cap (>= 1)."""
+    lib = _lib.load(); impl = resolve_impl(impl)
+    per = max(lib.bhnerf_acts_bytes(scene.ref, 1, impl), 1)
+    cap = DEFAULT_MAX_WORKSPACE if max_workspace is None else int(max_workspace)
+    return int(max(1, min(Bt, cap // per)))
 
 
 def adam_step(params, grads, mu, nu, count, lr_init=1e-4, lr_final=1e-6, num_iters=5000, b1=0.9, b2=0.999,

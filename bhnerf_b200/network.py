@@ -313,11 +313,23 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
                          scene.device).reshape(-1)
     A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
-    images, e, acts = engine.render_fwd(scene, state.flat, tf, impl, save_acts=True)
-    vis = engine.vis_fwd(A, images)
-    loss, dvis = engine.loss_vis(vis, target, sigma, float(scale), dtype)
-    dI = engine.vis_bwd(A, dvis, scene.P)
-    grads = engine.render_bwd(scene, state.flat, tf, dI, e, acts, impl)
+    # the chi^2 is separable per frame: process frame chunks whose saved activations fit the workspace cap
+    Bt = tf.numel()
+    Bc = engine.frames_per_chunk(scene, Bt, impl)
+    tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
+    sig = engine._dev_f32(sigma, scene.device)
+    loss, grads, imgs = None, None, []
+    for b0 in range(0, Bt, Bc):
+        sl = slice(b0, min(b0 + Bc, Bt))
+        images, e, acts = engine.render_fwd(scene, state.flat, tf[sl], impl, save_acts=True)
+        vis = engine.vis_fwd(A[sl].contiguous(), images)
+        l, dvis = engine.loss_vis(vis, tgt[sl], sig[sl], float(scale), dtype)
+        dI = engine.vis_bwd(A[sl].contiguous(), dvis, scene.P)
+        g = engine.render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)
+        loss = l if loss is None else loss + l             # sums of per-chunk partials (host-side plumbing)
+        grads = g if grads is None else grads + g
+        imgs.append(images)
+    images = imgs[0] if len(imgs) == 1 else torch.cat(imgs, dim=0)
     state = _pmean_and_apply(state, grads)
     return loss, state, _shape_images(images, scene, J)
 

@@ -145,6 +145,13 @@ int bhnerf_adam_step(float* params, const float* grads, float* mu, float* nu, in
                      int32_t count, float lr_init, float lr_final, int32_t transition_steps,
                      float b1, float b2, float eps, float grad_scale, void* stream);
 
+/* ---- accounting for benchmarks: kernels launched by this library, and (between begin/end) CUDA-event
+ * time per category {0 render fwd, 1 render bwd, 2 wgrad (SIMT only), 3 heads, 4 misc}.
+ * profile_end synchronises the device.  ms_host/scopes_host/launches_host: host arrays of 5.   */
+int64_t bhnerf_launch_count(void);
+int bhnerf_profile_begin(void);
+int bhnerf_profile_end(double* ms_host, int64_t* scopes_host, int64_t* launches_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+// Shared pieces of the tcgen05 kernel family (render_tc_fwd.cu, render_tc_bwd.cu): global workspace
+// layout, operand-image geometry, abortable mbarrier waits, bulk global->shared copies.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+// ---- operand images --------------------------------------------------------------------------
+// Every bf16 operand lives in the SWIZZLE_NONE canonical layout of 8x8 core matrices (128 B each).
+// "Row-group-major" image of R rows x C cols:  off(r,c) = (r/8)*128 + (c/8)*(R/8)*128 + (r%8)*16 + (c%8)*2
+//   * weights  W_l [k][n]      : R = K_l (padded), C = 128      (B operand; MN-major in fwd, K-major in dgrad)
+//   * samples  X   [s][c]      : R = 128 samples,  C = 128|32   (A operand K-major in fwd/dgrad, A/B MN-major in wgrad)
+// so a 128-row sample image has RS = 128 B, CS = 2048 B.
+#define TC_IMG_RS 128u
+#define TC_SIMG_CS 2048u                 // column-group stride of a 128-row sample image
+#define TC_SIMG_BYTES 32768u             // 128 x 128 bf16
+#define TC_FIMG_BYTES 8192u              // 128 x 32 bf16 (features, 21 real columns)
+
+__host__ __device__ constexpr uint32_t tc_layer_K(int l) { return l == 0 ? 32u : (l == 3 ? 160u : 128u); }
+__host__ __device__ constexpr uint32_t tc_plane_bytes(int l) { return tc_layer_K(l) * 128u * 2u; }   // one bf16 plane
+__host__ __device__ constexpr uint32_t tc_stage_bytes(int l) { return 2u * tc_plane_bytes(l); }      // [hi | lo]
+__host__ __device__ constexpr uint32_t tc_stage_off(int l) {                                         // in the weight block
+  return l == 0 ? 0u : (l == 1 ? 16384u : (l == 2 ? 81920u : 147456u));
+}
+#define TC_W_BYTES 229376u               // 16K + 64K + 64K + 80K
+#define TC_STAGE_MAX 81920u
+
+// ---- global workspace (bh_tc_ws_bytes) -------------------------------------------------------
+//   [0,256)        int32 status words (0 = ok)
+//   [256,4096)     fp32 constants: b0,b1,b2,b3 (4x128) | W4 (128) | b4 (1)
+//   [4096, +224K)  bf16 weight images, per layer [hi plane | lo plane]
+//   [262144, ...)  backward scratch (per-CTA gradient partials)
+#define TC_WS_STATUS 0u
+#define TC_WS_CONST 256u
+#define TC_WS_W 4096u
+#define TC_WS_BWD 262144u
+#define TC_CONST_FLOATS 768              // 641 used
+#define TC_C_B(l) ((l) * 128)
+#define TC_C_W4 512
+#define TC_C_B4 640
+
+namespace tc {
+using namespace umma;
+
+// ---- abortable waits: a wedged pipeline flags an error and drains instead of hanging the GPU ----
+struct Abort { volatile int* flag; };
+__device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, const Abort& ab) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((i & 255u) == 255u && *ab.flag) return false;
+  }
+  *ab.flag = 1;
+  return false;
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t sample_img_off(int row, int colgroup) {   // 16-byte chunk of 8 columns
+  return (uint32_t)(row >> 3) * TC_IMG_RS + (uint32_t)colgroup * TC_SIMG_CS + (uint32_t)(row & 7) * 16u;
+}
+
+// split 8 fp32 values into bf16 hi / lo chunks (16 B each)
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+    l[j] = pack_bf16x2(x[2 * j] - bf16_lo(h[j]), x[2 * j + 1] - bf16_hi(h[j]));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+}  // namespace tc

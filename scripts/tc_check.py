@@ -1,0 +1,66 @@
+"""GPU bring-up check of the tcgen05 family against the committed goldens and the fp32 SIMT family.
+Usage (on the B200 box): python scripts/tc_check.py [fwd|train]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bhnerf_b200 import constants, engine, synthetic, testing  # noqa: E402
+
+
+def status():
+    ws = engine._workspaces.get(torch.cuda.current_device())
+    return None if ws is None else ws[:16].view(torch.int32).tolist()
+
+
+def fwd_golden():
+    for case in ('case_image_full', 'case_lc_IQU'):
+        scene, d = testing.load_golden_scene(case)
+        params = torch.as_tensor(d['params_flat'], device='cuda')
+        tf = torch.as_tensor(d['t_frames'].astype(np.float32), device='cuda')
+        out = {}
+        for impl in ('simt', 'tc'):
+            img, e, _ = engine.render_fwd(scene, params, tf, impl)
+            torch.cuda.synchronize()
+            ref = d['images'] if d['images'].ndim == 4 else d['images'][:, None]
+            im = img.cpu().numpy().reshape(ref.shape)
+            out[impl] = (im, e)
+            print(case, impl, 'img rel err vs f64 oracle %.3e' % testing.rel_err(im, ref), 'status', status(), flush=True)
+        print(case, 'tc vs simt e max abs diff %.3e (max e %.3e)' % ((out['tc'][1] - out['simt'][1]).abs().max().item(),
+                                                                     out['simt'][1].abs().max().item()), flush=True)
+
+
+def fwd_big(name='cfg1_tutorial3', nt=8, reps=3):
+    c = synthetic.make_config(name, nt=nt)
+    rt, pr = c['rt'], c['predictor']
+    params = torch.as_tensor(synthetic.trained_like_flat_params(7)).cuda()
+    scene = engine.PackedScene(rt['coords'], rt['Omega'], rt['J'], rt['g'], rt['dtau'], rt['Sigma'], rt['t_geos'],
+                               rt['t_start_obs'], rt['t_injection'], pr['scale'], pr['rmin'], pr['rmax'], pr['z_width'],
+                               constants.GM_c3(t_units='hr'))
+    tf = torch.as_tensor(c['t_frames']).cuda()
+    res = {}
+    for impl in ('simt', 'tc'):
+        for save in (False, True):
+            img, e, acts = engine.render_fwd(scene, params, tf, impl, save_acts=save)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                img, e, acts = engine.render_fwd(scene, params, tf, impl, save_acts=save)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            n = nt * scene.n_active
+            print('%s %s save=%d: %.3f ms, %.3e eval samples/s, %.1f TFLOP/s algorithmic fwd, status %s' % (
+                name, impl, save, dt * 1e3, n / dt, n * 109312 / dt / 1e12, status()), flush=True)
+            res[impl] = img
+    print(name, 'tc vs simt images rel err %.3e' % ((res['tc'] - res['simt']).abs().max() / res['simt'].abs().max()).item(),
+          flush=True)
+
+
+if __name__ == '__main__':
+    what = sys.argv[1] if len(sys.argv) > 1 else 'fwd'
+    fwd_golden()
+    fwd_big('cfg1_tutorial3', 8)
+    fwd_big('cfg2_lp_flare', 16)

@@ -96,12 +96,13 @@ static int check_scene(const bhnerf_scene_t* sc, int Bt, int impl) {
   return 0;
 }
 
-static size_t acts_bytes_per_frame(const bhnerf_scene_t* sc, int impl) {
+// `pl` = precision plan of the TC family for this step (bh_tc_planes of the WHOLE step's frame count)
+static size_t acts_bytes_per_frame(const bhnerf_scene_t* sc, int impl, int pl) {
   return impl == BHNERF_IMPL_SIMT ? bh_simt_acts_floats_per_frame(sc->n_pad) * 4
-                                  : bh_tc_acts_bytes_per_frame(sc->n_pad);
+                                  : bh_tc_acts_bytes_per_frame(sc->n_pad, pl);
 }
 extern "C" size_t bhnerf_acts_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
-  return acts_bytes_per_frame(sc, impl) * (size_t)Bt;
+  return acts_bytes_per_frame(sc, impl, bh_tc_planes(sc->n_active, Bt)) * (size_t)Bt;
 }
 
 // fixed (frame-count independent) part of the backward workspace
@@ -109,8 +110,9 @@ static size_t bwd_fixed_bytes(int impl) {
   return impl == BHNERF_IMPL_SIMT ? align_up(BH_SIMT_WT_FLOATS * 4, 256) : align_up(bh_tc_ws_bytes(), 256);
 }
 // per-frame scratch of the backward beyond saved activations
-static size_t bwd_frame_bytes(const bhnerf_scene_t* sc, int impl) {
-  return impl == BHNERF_IMPL_SIMT ? bh_simt_delta_floats_per_frame(sc->n_pad) * 4 : 0;
+static size_t bwd_frame_bytes(const bhnerf_scene_t* sc, int impl, int pl) {
+  return impl == BHNERF_IMPL_SIMT ? bh_simt_delta_floats_per_frame(sc->n_pad) * 4
+                                  : bh_tc_delta_bytes_per_frame(sc->n_pad, pl);
 }
 
 // TC variant needs scratch for the bf16 weight images; the SIMT variant ignores it.
@@ -130,15 +132,15 @@ extern "C" int bhnerf_render_fwd(const bhnerf_scene_t* sc, const float* params, 
   } else {
     BH_REQUIRE(workspace && workspace_bytes >= bhnerf_fwd_workspace_bytes(impl), "render_fwd: workspace too small");
     if (int r = bh_tc_prepare_weights(params, workspace, st)) return r;
-    if (int r = bh_tc_fwd(v, fc, workspace, params, t_frames, Bt, e_out, acts_out, st)) return r;
+    if (int r = bh_tc_fwd(v, fc, workspace, params, t_frames, Bt, e_out, acts_out, bh_tc_planes(sc->n_active, Bt), st)) return r;
   }
   return bh_launch_ray_integrate(v, e_out, Bt, images, st);
 }
 
 extern "C" size_t bhnerf_bwd_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
   // enough for ONE frame of recompute; more lets the backward chunk more frames per launch
-  (void)Bt;
-  return bwd_fixed_bytes(impl) + acts_bytes_per_frame(sc, impl) + bwd_frame_bytes(sc, impl) +
+  const int pl = bh_tc_planes(sc->n_active, Bt);
+  return bwd_fixed_bytes(impl) + acts_bytes_per_frame(sc, impl, pl) + bwd_frame_bytes(sc, impl, pl) +
          (size_t)sc->n_pad * 4 + 1024;
 }
 
@@ -156,7 +158,8 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
   BH_REQUIRE(workspace_bytes >= fixed, "render_bwd: workspace too small");
   char* p = ws + fixed;
   size_t avail = workspace_bytes - fixed;
-  size_t per_frame = bwd_frame_bytes(sc, impl) + (acts_saved ? 0 : acts_bytes_per_frame(sc, impl)) +
+  const int pl = bh_tc_planes(sc->n_active, Bt);
+  size_t per_frame = bwd_frame_bytes(sc, impl, pl) + (acts_saved ? 0 : acts_bytes_per_frame(sc, impl, pl)) +
                      (e_saved && acts_saved ? 0 : (size_t)sc->n_pad * 4);
   int Bc = per_frame ? (int)(avail / per_frame) : Bt;
   if (Bc > Bt) Bc = Bt;
@@ -168,16 +171,16 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
   for (int b0 = 0; b0 < Bt; b0 += Bc) {
     int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
     char* q = p;
-    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl) * nb;
-    const void* acts = acts_saved ? (const char*)acts_saved + acts_bytes_per_frame(sc, impl) * b0 : nullptr;
+    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl, pl) * nb;
+    const void* acts = acts_saved ? (const char*)acts_saved + acts_bytes_per_frame(sc, impl, pl) * b0 : nullptr;
     const float* e = e_saved ? e_saved + (size_t)b0 * sc->n_pad : nullptr;
     if (recompute) {
-      void* acts_ws = q; q += acts_bytes_per_frame(sc, impl) * nb;
+      void* acts_ws = q; q += acts_bytes_per_frame(sc, impl, pl) * nb;
       float* e_ws = (float*)q;
       if (impl == BHNERF_IMPL_SIMT) {
         if (int r = bh_simt_fwd(v, fc, params, t_frames + b0, nb, e_ws, (float*)acts_ws, st)) return r;
       } else {
-        if (int r = bh_tc_fwd(v, fc, ws, params, t_frames + b0, nb, e_ws, acts_ws, st)) return r;
+        if (int r = bh_tc_fwd(v, fc, ws, params, t_frames + b0, nb, e_ws, acts_ws, pl, st)) return r;
       }
       acts = acts_ws; e = e_ws;
     }
@@ -185,20 +188,20 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
     if (impl == BHNERF_IMPL_SIMT) {
       if (int r = bh_simt_bwd(v, params, dI, nb, e, (const float*)acts, delta, (float*)ws, d_params, st)) return r;
     } else {
-      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, d_params, st)) return r;
+      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, delta, pl, d_params, st)) return r;
     }
   }
   return 0;
 }
 
 // ---- fused train step for separable image losses ----
-static size_t train_frame_bytes(const bhnerf_scene_t* sc, int impl) {
-  return acts_bytes_per_frame(sc, impl) + bwd_frame_bytes(sc, impl) + (size_t)sc->n_pad * 4 +
+static size_t train_frame_bytes(const bhnerf_scene_t* sc, int impl, int pl) {
+  return acts_bytes_per_frame(sc, impl, pl) + bwd_frame_bytes(sc, impl, pl) + (size_t)sc->n_pad * 4 +
          (size_t)sc->S * sc->P * 4;
 }
 extern "C" size_t bhnerf_train_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
   // all Bt frames in one chunk; smaller workspaces are accepted down to one frame
-  return bwd_fixed_bytes(impl) + train_frame_bytes(sc, impl) * (size_t)Bt + 1024;
+  return bwd_fixed_bytes(impl) + train_frame_bytes(sc, impl, bh_tc_planes(sc->n_active, Bt)) * (size_t)Bt + 1024;
 }
 
 int bh_loss_image_accum(const float* images, const float* target, const float* sigma, const float* offset,
@@ -218,7 +221,8 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
   FrameConsts fc = frame_consts(sc);
   char* ws = (char*)workspace;
   size_t fixed = bwd_fixed_bytes(impl);
-  size_t per_frame = train_frame_bytes(sc, impl);
+  const int pl = bh_tc_planes(sc->n_active, Bt);
+  size_t per_frame = train_frame_bytes(sc, impl, pl);
   BH_REQUIRE(workspace_bytes >= fixed + per_frame, "train_step_image: workspace (%zu B) cannot hold one frame (%zu B)",
              workspace_bytes, fixed + per_frame);
   int Bc = (int)((workspace_bytes - fixed) / per_frame);
@@ -230,15 +234,15 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
   for (int b0 = 0; b0 < Bt; b0 += Bc) {
     int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
     char* q = ws + fixed;
-    void* acts = q; q += acts_bytes_per_frame(sc, impl) * nb;
-    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl) * nb;
+    void* acts = q; q += acts_bytes_per_frame(sc, impl, pl) * nb;
+    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl, pl) * nb;
     float* e = (float*)q; q += (size_t)sc->n_pad * 4 * nb;
     float* dI = (float*)q;
     float* img = images + (size_t)b0 * sc->S * sc->P;
     if (impl == BHNERF_IMPL_SIMT) {
       if (int r = bh_simt_fwd(v, fc, params, t_frames + b0, nb, e, (float*)acts, st)) return r;
     } else {
-      if (int r = bh_tc_fwd(v, fc, ws, params, t_frames + b0, nb, e, acts, st)) return r;
+      if (int r = bh_tc_fwd(v, fc, ws, params, t_frames + b0, nb, e, acts, pl, st)) return r;
     }
     if (int r = bh_launch_ray_integrate(v, e, nb, img, st)) return r;
     if (int r = bh_loss_image_accum(img, target + b0 * tstride, sigma + b0 * tstride, offset + b0 * tstride,
@@ -246,7 +250,7 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
     if (impl == BHNERF_IMPL_SIMT) {
       if (int r = bh_simt_bwd(v, params, dI, nb, e, (const float*)acts, delta, (float*)ws, d_params, st)) return r;
     } else {
-      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, d_params, st)) return r;
+      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, delta, pl, d_params, st)) return r;
     }
   }
   return 0;

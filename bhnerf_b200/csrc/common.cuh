@@ -141,12 +141,14 @@ int bh_simt_bwd(const PackedView& v, const float* params, const float* d_images 
                 float* d_params /*accumulated into*/, cudaStream_t st);
 #define BH_SIMT_WT_FLOATS (3 * 128 * 128)
 
-// TC (tcgen05) family
-size_t bh_tc_acts_bytes_per_frame(int n_pad);
-size_t bh_tc_ws_bytes();                                     // weight images + grad partials
+// TC (tcgen05) family.  `planes` = bf16 planes kept of every saved activation / cotangent (1: hi, 2: hi+lo).
+int bh_tc_planes(int n_active, int Bt_total);               // precision plan of a step
+size_t bh_tc_acts_bytes_per_frame(int n_pad, int planes);
+size_t bh_tc_delta_bytes_per_frame(int n_pad, int planes); // backward scratch (delta images)
+size_t bh_tc_ws_bytes();                                     // weight images + status words
 int bh_tc_prepare_weights(const float* params, void* ws, cudaStream_t st);
 int bh_tc_fwd(const PackedView& v, const FrameConsts& fc, const void* ws, const float* params,
-              const float* t_frames, int Bt, float* e_out, void* acts /*or null*/, cudaStream_t st);
+              const float* t_frames, int Bt, float* e_out, void* acts /*or null*/, int planes, cudaStream_t st);
 int bh_tc_bwd(const PackedView& v, const void* ws, const float* params, const float* d_images, int Bt,
-              const float* e_saved, const void* acts, float* d_params /*accumulated into*/,
+              const float* e_saved, const void* acts, void* delta_ws, int planes, float* d_params /*accumulated into*/,
               cudaStream_t st);

@@ -12,6 +12,8 @@
 // the CUDA cores run the bias+ReLU+hi/lo-split epilogue of the other.  Activations never leave the SM:
 // D (fp32) is read from TMEM with tcgen05.ld and the next layer's A operand is written back to TMEM with
 // tcgen05.st (TS-form MMA); only the 21 posenc features go through shared memory (SS-form, K-major).
+#include <cuda_fp16.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -50,12 +52,21 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ params, uint
   const int woff[4] = {OFF_W0, OFF_W1, OFF_W2, OFF_W3};
   const int krows[4] = {21, 128, 128, 149};
   float w = (k < krows[l]) ? params[woff[l] + k * 128 + n] : 0.f;
-  __nv_bfloat16 hi = __float2bfloat16_rn(w);
-  __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
   uint32_t off = img_off(k, n, TC_IMG_RS, (uint32_t)(K / 8) * 128u);
-  uint8_t* base = ws + TC_WS_W + tc_stage_off(l);
-  *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(base + tc_plane_bytes(l) + off) = lo;
+  {   // forward: fp16 hi/lo planes
+    __half hi = __float2half_rn(w);
+    __half lo = __float2half_rn(w - __half2float(hi));
+    uint8_t* base = ws + TC_WS_W + tc_stage_off(l);
+    *reinterpret_cast<__half*>(base + off) = hi;
+    *reinterpret_cast<__half*>(base + tc_plane_bytes(l) + off) = lo;
+  }
+  {   // dgrad chain: bf16 hi/lo planes
+    __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    uint8_t* base = ws + TC_WS_WB + tc_stage_off(l);
+    *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + tc_plane_bytes(l) + off) = lo;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -89,7 +100,7 @@ __device__ __forceinline__ void issue_layer(int l, uint32_t tmem_d, uint32_t tme
   }
 }
 
-template <int NPASS, bool SAVE>
+template <int NPASS, int SAVE>      // SAVE = bf16 planes of every activation kept for the backward (0, 1, 2)
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, const float* __restrict__ t_frames,
               int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts, int* __restrict__ status) {
@@ -110,7 +121,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
     mbar_init(&bars[BAR_WEMPTY + 0], 1); mbar_init(&bars[BAR_WEMPTY + 1], 1);
     mbar_init(&bars[BAR_AREADY + 0], 4); mbar_init(&bars[BAR_AREADY + 1], 4);
     mbar_init(&bars[BAR_DREADY + 0], 1); mbar_init(&bars[BAR_DREADY + 1], 1);
-    *abort_s = 0;
+    abort_s[0] = 0; abort_s[1] = 0;
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(tmem_base_s, 512);
@@ -142,7 +153,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, 128, 0, 1);
+      const uint32_t idesc = make_idesc_f16(128, 128, 0, 1);
       uint32_t wcnt = 0, a_phase[2] = {0u, 0u};
       for (int r = 0;; ++r) {
         int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
@@ -189,18 +200,27 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
       const bool valid = bh_features(v.x[i], v.y[i], v.z[i], v.omega[i], v.tgeo[i], tfc, fc, f);
 #pragma unroll
       for (int k = BH_NF; k < 32; ++k) f[k] = 0.f;
+      // column 21 = 1: the weight images have zero rows there, and the wgrad kernel reads bias gradients off it
+      if (SAVE) f[TC_ONES_COL] = 1.f;
+      uint8_t* feat_save = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) +
+                                      (size_t)v.n_pad * 1024u * SAVE + (size_t)tile * TC_FIMG_BYTES : nullptr;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint4 hi, lo;
-        split8(f + 8 * g, hi, lo);
+        split8_f16(f + 8 * g, hi, lo);
         uint32_t off = sample_img_off(row, g);
         *reinterpret_cast<uint4*>(my_feat + off) = hi;
         if (NPASS > 1) *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + off) = lo;
+        if (SAVE) {                                     // the backward's operands are bf16 (range of the cotangents)
+          split8(f + 8 * g, hi, lo);
+          *reinterpret_cast<uint4*>(feat_save + off) = hi;
+          if (SAVE == 2) *reinterpret_cast<uint4*>(feat_save + (size_t)v.n_pad * 64u + off) = lo;
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_AREADY + slot]);
-      uint8_t* act_tile = SAVE ? acts + (size_t)b * ((size_t)v.n_pad * 1024u) + (size_t)tile * TC_SIMG_BYTES : nullptr;
+      uint8_t* act_tile = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + (size_t)tile * TC_SIMG_BYTES : nullptr;
       float o = cst[TC_C_B4];
       for (int l = 0; l < 4; ++l) {
         ok = wait(&bars[BAR_DREADY + slot], d_phase, ab);
@@ -218,12 +238,12 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(raw[j]) + bias[c0 + j], 0.f);
           uint32_t hi[16], lo[16];
+          if (l < 3) {                                  // next layer's A operand: fp16 hi/lo planes in TMEM
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            hi[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-            if (NPASS > 1) lo[j] = pack_bf16x2(x[2 * j] - bf16_lo(hi[j]), x[2 * j + 1] - bf16_hi(hi[j]));
-          }
-          if (l < 3) {
+            for (int j = 0; j < 16; ++j) {
+              hi[j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
+              if (NPASS > 1) lo[j] = pack_f16x2(x[2 * j] - f16_lo(hi[j]), x[2 * j + 1] - f16_hi(hi[j]));
+            }
             tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), hi);
             if (NPASS > 1) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), lo);
           } else {
@@ -231,11 +251,20 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) o = fmaf(x[j], w4[j], o);
           }
-          if (SAVE) {
+          if (SAVE) {                                   // saved for the backward as bf16 planes
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int j = 0; j < 16; ++j) {
+              hi[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+              if (SAVE == 2) lo[j] = pack_bf16x2(x[2 * j] - bf16_lo(hi[j]), x[2 * j + 1] - bf16_hi(hi[j]));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
               *reinterpret_cast<uint4*>(act_img + sample_img_off(row, (c0 >> 3) + g)) =
                   make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+              if (SAVE == 2)
+                *reinterpret_cast<uint4*>(act_img + (size_t)v.n_pad * 1024u + sample_img_off(row, (c0 >> 3) + g)) =
+                    make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+            }
           }
         }
         if (l < 3) {
@@ -247,6 +276,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
       }
       if (!ok) break;
       float e = bh_sigmoid_m10(o);
+      if (!(fabsf(o) <= 3.0e38f)) abort_s[1] = 1;      // fp16 operand overflow (|activation| > 65504): flag, do not hide
       e_out[(size_t)b * v.n_pad + i] = (valid && v.ray[i] >= 0) ? e : 0.f;     // network.py:232
     }
   }
@@ -254,6 +284,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
   __syncthreads();
   if (warp == 8) tmem_dealloc(tbase, 512);
   if (tid == 0 && *abort_s) atomicExch(status, 1);
+  if (tid == 0 && abort_s[1]) atomicExch(status + 3, 1);
 }
 
 int g_num_sms = 0;
@@ -266,7 +297,7 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int NPASS, bool SAVE>
+template <int NPASS, int SAVE>
 int launch_fwd(const PackedView& v, const FrameConsts& fc, const void* ws, const float* t_frames, int Bt,
                float* e_out, void* acts, cudaStream_t st) {
   auto kern = tc_fwd_kernel<NPASS, SAVE>;
@@ -281,7 +312,21 @@ int launch_fwd(const PackedView& v, const FrameConsts& fc, const void* ws, const
 
 }  // namespace
 
-size_t bh_tc_acts_bytes_per_frame(int n_pad) { return (size_t)n_pad * 1024; }   // h0..h3 hi planes (bf16)
+size_t bh_tc_acts_bytes_per_frame(int n_pad, int planes) { return tc_acts_bytes_per_frame(n_pad, planes); }
+
+// Precision plan of the backward: the saved activations / cotangents are bf16.  With the hi plane
+// only, the rounding noise of the wgrad reduction averages out as 1/sqrt(#sample-frames) (measured 1e-4 of the
+// gradient at 4.5e6 sample-frames); below 2^19 sample-frames per step both planes are kept (x3 products, error
+// ~1e-5 at any size).  BHNERF_TC_PLANES=1|2 overrides.
+int bh_tc_planes(int n_active, int Bt_total) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("BHNERF_TC_PLANES");
+    forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+  }
+  if (forced) return forced;
+  return ((long long)n_active * (long long)Bt_total < (1ll << 19)) ? 2 : 1;
+}
 size_t bh_tc_ws_bytes() { return 1u << 20; }
 
 int bh_tc_prepare_weights(const float* params, void* ws, cudaStream_t st) {
@@ -292,15 +337,11 @@ int bh_tc_prepare_weights(const float* params, void* ws, cudaStream_t st) {
 }
 
 int bh_tc_fwd(const PackedView& v, const FrameConsts& fc, const void* ws, const float* params,
-              const float* t_frames, int Bt, float* e_out, void* acts, cudaStream_t st) {
+              const float* t_frames, int Bt, float* e_out, void* acts, int planes, cudaStream_t st) {
   (void)params;
   BhProfScope ps(BH_CAT_FWD, 1, st);
-  return acts ? launch_fwd<3, true>(v, fc, ws, t_frames, Bt, e_out, acts, st)
-              : launch_fwd<3, false>(v, fc, ws, t_frames, Bt, e_out, nullptr, st);
+  if (!acts) return launch_fwd<3, 0>(v, fc, ws, t_frames, Bt, e_out, nullptr, st);
+  return planes == 2 ? launch_fwd<3, 2>(v, fc, ws, t_frames, Bt, e_out, acts, st)
+                     : launch_fwd<3, 1>(v, fc, ws, t_frames, Bt, e_out, acts, st);
 }
 
-int bh_tc_bwd(const PackedView&, const void*, const float*, const float*, int, const float*, const void*, float*,
-              cudaStream_t) {
-  bh_set_error("TC backward kernels not built yet");
-  return 3;
-}

@@ -1,0 +1,452 @@
+// tcgen05 backward of the render (sm_100a): parameter gradient of image_plane_prediction
+// (jax.value_and_grad pull-back, bhnerf/network.py:617,:677) from the activations the forward kernel saved.
+//
+//   tc_dgrad_kernel : d images -> d o -> delta_3 .. delta_0 (pre-activation cotangents), one 128-sample tile per
+//                     slot, two slots ping-pong.  delta_{l-1} = (delta_l * W_l[:128]^T) .* (h_{l-1} > 0) runs on the
+//                     tensor cores with delta_l (bf16) as the TMEM A operand and the forward's weight images
+//                     read K-major (two passes: W hi + W lo planes; DESIGN.md s4 "x2w").  All three hidden
+//                     weight layers stay resident in shared memory (208 KB, loaded once per CTA).
+//   tc_wgrad_kernel : dW_l^T[n][k] = sum_s delta_l[s][n] * in_l[s][k] as MN-major x MN-major UMMAs over the sample
+//                     axis, accumulated in TMEM (496 of 512 columns) across all tiles of a persistent CTA; bias
+//                     gradients ride on the constant-one column of the feature image, dW4 on the aux image.
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+// =====================================================================================================
+// dgrad chain
+// =====================================================================================================
+constexpr int kDThreads = 320;
+constexpr uint32_t DW_BYTES = TC_W_BYTES - 16384u;                 // stages of layers 1..3, contiguous in ws
+constexpr uint32_t D_SM_W = 0;
+constexpr uint32_t D_SM_W4 = DW_BYTES;                             // 128 floats
+constexpr uint32_t D_SM_BARS = D_SM_W4 + 512;
+constexpr uint32_t D_SM_TOTAL = D_SM_BARS + 128;
+enum { DB_WFULL = 0, DB_AREADY = 1, DB_DREADY = 3 };
+
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t h2, uint32_t d2) {   // keep the bf16 halves of d2 where h2 > 0
+  uint32_t m = ((h2 & 0x00007fffu) ? 0x0000ffffu : 0u) | ((h2 & 0x7fff0000u) ? 0xffff0000u : 0u);
+  return d2 & m;
+}
+
+// split two fp32 cotangents into packed bf16 hi / lo words and apply the relu mask of the packed activations h2
+template <int PL>
+__device__ __forceinline__ void delta_pack(uint32_t h2, float a, float b, uint32_t& hi, uint32_t& lo) {
+  uint32_t p = pack_bf16x2(a, b);
+  hi = relu_mask2(h2, p);
+  if (PL == 2) lo = relu_mask2(h2, pack_bf16x2(a - bf16_lo(p), b - bf16_hi(p)));
+}
+
+template <int PL>
+__global__ void __launch_bounds__(kDThreads, 1)
+tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
+                const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
+                float* __restrict__ d_params, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* wsm = smem + D_SM_W;
+  float* w4s = (float*)(smem + D_SM_W4);
+  uint64_t* bars = (uint64_t*)(smem + D_SM_BARS);
+  uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
+  int* abort_s = (int*)(tmem_base_s + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per_frame = v.n_pad / 128;
+  const int NT = Bt * tiles_per_frame;
+  Abort ab{abort_s};
+
+  if (tid == 0) {
+    mbar_init(&bars[DB_WFULL], 1);
+    mbar_init(&bars[DB_AREADY + 0], 4); mbar_init(&bars[DB_AREADY + 1], 4);
+    mbar_init(&bars[DB_DREADY + 0], 1); mbar_init(&bars[DB_DREADY + 1], 1);
+    *abort_s = 0;
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_base_s, 512);
+  if (tid < 128) w4s[tid] = ((const float*)(ws + TC_WS_CONST))[TC_C_W4 + tid];
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tbase = *tmem_base_s;
+
+  if (warp == 9) {
+    if (lane == 0) {      // resident weights: layers 1..3 [hi|lo] images, one shot
+      mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
+      const uint8_t* src = ws + TC_WS_WB + 16384u;
+      bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
+      bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
+      bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, 128, 0, 0);      // A from TMEM, B K-major
+      uint32_t a_phase[2] = {0u, 0u};
+      bool ok = wait(&bars[DB_WFULL], 0, ab);
+      for (int r = 0; ok; ++r) {
+        int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
+        if (T0 >= NT) break;
+        for (int l = 3; l >= 1 && ok; --l) {
+          const uint32_t wl = smem_u32(wsm) + tc_stage_off(l) - 16384u;
+          const uint32_t plane = tc_plane_bytes(l), cs = (tc_layer_K(l) / 8u) * 128u;
+          for (int s = 0; s < 2; ++s) {
+            if (T0 + s >= NT) continue;
+            ok = wait(&bars[DB_AREADY + s], a_phase[s], ab);
+            if (!ok) break;
+            a_phase[s] ^= 1u;
+            tc_fence_after_sync();
+            const uint32_t td = tbase + (uint32_t)s * 256u, ta = td + 128u;
+            uint32_t acc = 0;
+            // passes: d_hi*W_hi, d_hi*W_lo, and with both planes d_lo*W_hi
+#pragma unroll 1
+            for (uint32_t p = 0; p < (PL == 2 ? 3u : 2u); ++p)
+#pragma unroll 1
+              for (uint32_t ks = 0; ks < 8; ++ks) {
+                // B' [K'=n][N'=k] = W_l[k][n]: the forward image read K-major (K' groups = column groups)
+                uint64_t bd = make_desc(wl + (p == 1 ? plane : 0u) + ks * 2u * cs, cs, TC_IMG_RS);
+                mma_ts(td, ta + (p == 2 ? 64u : 0u) + ks * 8u, bd, idesc, acc);
+                acc = 1;
+              }
+            mma_commit(&bars[DB_DREADY + s]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int slot = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    const uint32_t t_lane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 256u;
+    uint32_t d_phase = 0;
+    float db4 = 0.f;
+    bool ok = true;
+    const size_t act_fs = tc_acts_bytes_per_frame(v.n_pad, PL), del_fs = tc_delta_bytes_per_frame(v.n_pad, PL);
+    const size_t lstride = (size_t)v.n_pad * 256u, pstride = (size_t)v.n_pad * 1024u;
+    for (int r = 0; ok; ++r) {
+      int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
+      if (T0 >= NT) break;
+      int T = T0 + slot;
+      if (T >= NT) continue;
+      const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
+      const int i = tile * 128 + row;
+      const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
+      uint8_t* del_tile = deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+      // d loss / d o = e(1-e) * sum_c dI[b,c,ray] * w[c,i]   (sigmoid', network.py:230; kgeo.py:621)
+      const int ray = v.ray[i];
+      const float e = e_saved[(size_t)b * v.n_pad + i];
+      float g = 0.f;
+      if (ray >= 0)
+        for (int c = 0; c < v.S; ++c) g += d_images[((size_t)b * v.S + c) * v.P + ray] * v.w[(size_t)c * v.n_pad + i];
+      const float dout = g * e * (1.f - e);
+      db4 += dout;
+      {   // aux image [128][16]: col 0 = bf16 hi part of dout, col 1 = lo part
+        uint8_t* aux = deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
+        const float dh = __bfloat162float(__float2bfloat16_rn(dout));
+        *reinterpret_cast<uint4*>(aux + sample_img_off(row, 0)) = make_uint4(pack_bf16x2(dh, dout - dh), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(aux + sample_img_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      // delta_3[j] = dout * W4[j] * (h3[j] > 0)
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t d[16], dl[16];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const uint32_t off = sample_img_off(row, (c0 >> 3) + gq);
+          uint4 h = *reinterpret_cast<const uint4*>(act_tile + 3 * lstride + off);
+          const float* w4 = w4s + c0 + 8 * gq;
+          delta_pack<PL>(h.x, dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
+          delta_pack<PL>(h.y, dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
+          delta_pack<PL>(h.z, dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
+          delta_pack<PL>(h.w, dout * w4[6], dout * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
+          *reinterpret_cast<uint4*>(del_tile + 3 * lstride + off) =
+              make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]);
+          if (PL == 2)
+            *reinterpret_cast<uint4*>(del_tile + pstride + 3 * lstride + off) =
+                make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
+        }
+        tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), d);
+        if (PL == 2) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), dl);
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
+      for (int l = 3; l >= 1; --l) {       // D = delta_l * W_l^T  ->  delta_{l-1}
+        ok = wait(&bars[DB_DREADY + slot], d_phase, ab);
+        if (!ok) break;
+        d_phase ^= 1u;
+        tc_fence_after_sync();
+        const uint8_t* h_img = act_tile + (size_t)(l - 1) * lstride;
+        uint8_t* d_img = del_tile + (size_t)(l - 1) * lstride;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t raw[32], d[16], dl[16];
+          tmem_ld32(t_lane + (uint32_t)c0, raw);
+          tmem_wait_ld();
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const uint32_t off = sample_img_off(row, (c0 >> 3) + gq);
+            uint4 h = *reinterpret_cast<const uint4*>(h_img + off);
+            const uint32_t* rr = raw + 8 * gq;
+            delta_pack<PL>(h.x, __uint_as_float(rr[0]), __uint_as_float(rr[1]), d[4 * gq + 0], dl[4 * gq + 0]);
+            delta_pack<PL>(h.y, __uint_as_float(rr[2]), __uint_as_float(rr[3]), d[4 * gq + 1], dl[4 * gq + 1]);
+            delta_pack<PL>(h.z, __uint_as_float(rr[4]), __uint_as_float(rr[5]), d[4 * gq + 2], dl[4 * gq + 2]);
+            delta_pack<PL>(h.w, __uint_as_float(rr[6]), __uint_as_float(rr[7]), d[4 * gq + 3], dl[4 * gq + 3]);
+            *reinterpret_cast<uint4*>(d_img + off) = make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]);
+            if (PL == 2)
+              *reinterpret_cast<uint4*>(d_img + pstride + off) =
+                  make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
+          }
+          if (l > 1) {
+            tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), d);
+            if (PL == 2) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), dl);
+          }
+        }
+        if (l > 1) {
+          tmem_wait_st();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
+        }
+      }
+    }
+    // d b4 = sum dout (network.py:64 bias of the last Dense)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) db4 += __shfl_xor_sync(0xffffffffu, db4, o);
+    if (lane == 0 && db4 != 0.f) atomicAdd(d_params + OFF_B4, db4);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tbase, 512);
+  if (tid == 0 && *abort_s) atomicExch(status + 1, 1);
+}
+
+// =====================================================================================================
+// wgrad
+// =====================================================================================================
+constexpr int kWThreads = 192;             // warps 0-3 final epilogue, warp 4 MMA issuer, warp 5 producer
+constexpr uint32_t W_SM_STAGE = 0;                                            // kWStages x [A 32K | B 32K]
+template <int PL> struct WCfg {
+  static constexpr int kWStages = PL == 2 ? 2 : 3;                            // the two-plane plan is for small steps
+  static constexpr uint32_t W_FBUF = PL * TC_FIMG_BYTES + TC_AIMG_BYTES;      // [feat hi 8K | (feat lo 8K) | aux 4K]
+  static constexpr uint32_t SM_FEAT = kWStages * 2 * TC_SIMG_BYTES;           // 2 x W_FBUF
+  static constexpr uint32_t SM_BARS = SM_FEAT + 2 * W_FBUF;
+  static constexpr uint32_t SM_TOTAL = SM_BARS + 256;
+};
+enum { WB_FULL = 0, WB_EMPTY = 3, WB_FFULL = 6, WB_FEMPTY = 8, WB_DONE = 10 };
+// TMEM accumulator columns (lane = n, or j for dW4)
+constexpr uint32_t ACC_W3 = 0, ACC_W3F = 128, ACC_W2 = 160, ACC_W1 = 288, ACC_W0F = 416, ACC_B2 = 448, ACC_B1 = 464,
+                   ACC_W4 = 480;
+
+// Per tile the CTA runs a list of stage fills ("sub-jobs").  job j picks the operands
+//   0: delta_3 x h2 (+feat)   1: delta_2 x h1 (+ones)   2: delta_1 x h0 (+ones)   3: delta_0 x feat   4: h3 x aux
+// and with two planes every job runs its bf16 plane combinations (A plane pa, B plane pb):
+//   jobs 0-3: (hi,hi) (lo,hi) (hi,lo)      job 4: (hi,-) (lo,-)   [aux carries both parts of dout]
+template <int PL> __device__ __forceinline__ int wg_num_subjobs() { return PL == 2 ? 14 : 5; }
+template <int PL> __device__ __forceinline__ void wg_subjob(int idx, int& j, int& pa, int& pb) {
+  if (PL == 1) { j = idx; pa = 0; pb = 0; return; }
+  if (idx < 12) { j = idx / 3; int c = idx - 3 * j; pa = (c == 1); pb = (c == 2); }
+  else { j = 4; pa = idx - 12; pb = 0; }
+}
+
+template <int PL>
+__global__ void __launch_bounds__(kWThreads, 1)
+tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas,
+                float* __restrict__ d_params, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kWStages = WCfg<PL>::kWStages;
+  constexpr uint32_t W_SM_FEAT = WCfg<PL>::SM_FEAT, W_SM_BARS = WCfg<PL>::SM_BARS, W_FBUF = WCfg<PL>::W_FBUF;
+  uint64_t* bars = (uint64_t*)(smem + W_SM_BARS);
+  uint32_t* tmem_base_s = (uint32_t*)(bars + 12);
+  int* abort_s = (int*)(tmem_base_s + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per_frame = n_pad / 128;
+  const int NT = Bt * tiles_per_frame;
+  Abort ab{abort_s};
+  const size_t act_fs = tc_acts_bytes_per_frame(n_pad, PL), del_fs = tc_delta_bytes_per_frame(n_pad, PL);
+  const size_t lstride = (size_t)n_pad * 256u, pstride = (size_t)n_pad * 1024u;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWStages; ++s) { mbar_init(&bars[WB_FULL + s], 1); mbar_init(&bars[WB_EMPTY + s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars[WB_FFULL + s], 1); mbar_init(&bars[WB_FEMPTY + s], 1); }
+    mbar_init(&bars[WB_DONE], 1);
+    *abort_s = 0;
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tbase = *tmem_base_s;
+  const bool has_work = (int)blockIdx.x < NT;
+
+  if (warp == 5) {
+    // ===================== producer: bulk copies of the saved images =====================
+    if (lane == 0) {
+      uint32_t cnt = 0, fcnt = 0;
+      bool ok = true;
+      for (int T = blockIdx.x; T < NT && ok; T += gridDim.x, ++fcnt) {
+        const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
+        const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
+        const uint8_t* del_tile = deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+        {   // feature (+ lo plane) and aux images of this tile
+          uint32_t fs = fcnt & 1u;
+          ok = wait(&bars[WB_FEMPTY + fs], ((fcnt >> 1) & 1u) ^ 1u, ab);
+          if (!ok) break;
+          uint8_t* dst = smem + W_SM_FEAT + fs * W_FBUF;
+          const uint8_t* fsrc = acts + (size_t)b * act_fs + pstride * PL + (size_t)tile * TC_FIMG_BYTES;
+          mbar_expect_tx(&bars[WB_FFULL + fs], PL * TC_FIMG_BYTES + TC_AIMG_BYTES);
+          bulk_g2s(dst, fsrc, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
+          if (PL == 2) bulk_g2s(dst + TC_FIMG_BYTES, fsrc + (size_t)n_pad * 64u, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
+          bulk_g2s(dst + PL * TC_FIMG_BYTES, deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES,
+                   TC_AIMG_BYTES, &bars[WB_FFULL + fs]);
+        }
+        for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
+          int j, pa, pb;
+          wg_subjob<PL>(idx, j, pa, pb);
+          uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
+          ok = wait(&bars[WB_EMPTY + st], ph ^ 1u, ab);
+          if (!ok) break;
+          uint8_t* dst = smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES;
+          const uint8_t* a_src = (j < 4) ? del_tile + pa * pstride + (size_t)(3 - j) * lstride
+                                         : act_tile + pa * pstride + 3 * lstride;
+          mbar_expect_tx(&bars[WB_FULL + st], (j < 3) ? 2 * TC_SIMG_BYTES : TC_SIMG_BYTES);
+          bulk_g2s(dst, a_src, TC_SIMG_BYTES, &bars[WB_FULL + st]);
+          if (j < 3)
+            bulk_g2s(dst + TC_SIMG_BYTES, act_tile + pb * pstride + (size_t)(2 - j) * lstride, TC_SIMG_BYTES,
+                     &bars[WB_FULL + st]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t id128 = make_idesc(128, 128, 1, 1), id32 = make_idesc(128, 32, 1, 1), id16 = make_idesc(128, 16, 1, 1);
+      uint32_t cnt = 0, fcnt = 0;
+      bool ok = true;
+      uint32_t later_tile = 0;               // 0 for the CTA's first tile: accumulators start from zero
+      // all operands are [s][c] images read MN-major: K (= sample) groups advance by RS, M/N groups by CS
+      auto desc = [](uint32_t base, uint32_t ks) { return make_desc(base + ks * 2u * TC_IMG_RS, TC_IMG_RS, TC_SIMG_CS); };
+      for (int T = blockIdx.x; T < NT && ok; T += gridDim.x, ++fcnt, later_tile = 1) {
+        uint32_t fs = fcnt & 1u;
+        ok = wait(&bars[WB_FFULL + fs], (fcnt >> 1) & 1u, ab);
+        if (!ok) break;
+        const uint32_t fbuf = smem_u32(smem + W_SM_FEAT + fs * W_FBUF);
+        const uint32_t aux = fbuf + PL * TC_FIMG_BYTES;
+        for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
+          int j, pa, pb;
+          wg_subjob<PL>(idx, j, pa, pb);
+          uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
+          ok = wait(&bars[WB_FULL + st], ph, ab);
+          if (!ok) break;
+          tc_fence_after_sync();
+          const uint32_t A = smem_u32(smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES), B = A + TC_SIMG_BYTES;
+          const uint32_t feat = fbuf + (uint32_t)pb * TC_FIMG_BYTES;
+          const uint32_t started = later_tile | ((pa | pb) ? 1u : 0u);     // (hi,hi) is each accumulator's first product
+#pragma unroll 1
+          for (uint32_t ks = 0; ks < 8; ++ks) {
+            const uint32_t acc = started | (ks > 0 ? 1u : 0u);
+            const uint64_t ad = desc(A, ks);
+            if (j == 0) {
+              mma_ss(tbase + ACC_W3, ad, desc(B, ks), id128, acc);
+              mma_ss(tbase + ACC_W3F, ad, desc(feat, ks), id32, acc);
+            } else if (j == 1) {
+              mma_ss(tbase + ACC_W2, ad, desc(B, ks), id128, acc);
+              if (pb == 0) mma_ss(tbase + ACC_B2, ad, desc(fbuf + 2u * TC_SIMG_CS, ks), id16, acc);
+            } else if (j == 2) {
+              mma_ss(tbase + ACC_W1, ad, desc(B, ks), id128, acc);
+              if (pb == 0) mma_ss(tbase + ACC_B1, ad, desc(fbuf + 2u * TC_SIMG_CS, ks), id16, acc);
+            } else if (j == 3) {
+              mma_ss(tbase + ACC_W0F, ad, desc(feat, ks), id32, acc);
+            } else {
+              mma_ss(tbase + ACC_W4, ad, desc(aux, ks), id16, acc);
+            }
+          }
+          mma_commit(&bars[WB_EMPTY + st]);
+        }
+        if (ok) mma_commit(&bars[WB_FEMPTY + fs]);
+      }
+      mma_commit(&bars[WB_DONE]);
+    }
+    __syncwarp();
+  } else if (has_work) {
+    // ===================== final epilogue: TMEM accumulators -> d_params (atomic accumulate) =====================
+    bool ok = wait(&bars[WB_DONE], 0, ab);
+    tc_fence_after_sync();
+    if (ok) {
+      const int n = warp * 32 + lane;
+      const uint32_t t_lane = tbase + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < 496; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(t_lane + c0, raw);
+        tmem_wait_ld();
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const uint32_t c = c0 + (uint32_t)jj;
+          const float val = __uint_as_float(raw[jj]);
+          int dst = -1;
+          if (c < ACC_W3F) dst = OFF_W3 + (int)c * 128 + n;
+          else if (c < ACC_W2) { int kf = (int)(c - ACC_W3F); dst = kf < BH_NF ? OFF_W3 + (128 + kf) * 128 + n : (kf == TC_ONES_COL ? OFF_B3 + n : -1); }
+          else if (c < ACC_W1) dst = OFF_W2 + (int)(c - ACC_W2) * 128 + n;
+          else if (c < ACC_W0F) dst = OFF_W1 + (int)(c - ACC_W1) * 128 + n;
+          else if (c < ACC_B2) { int kf = (int)(c - ACC_W0F); dst = kf < BH_NF ? OFF_W0 + kf * 128 + n : (kf == TC_ONES_COL ? OFF_B0 + n : -1); }
+          else if (c < ACC_B1) dst = (c - ACC_B2 == TC_ONES_COL - 16) ? OFF_B2 + n : -1;
+          else if (c < ACC_W4) dst = (c - ACC_B1 == TC_ONES_COL - 16) ? OFF_B1 + n : -1;
+          else dst = (c <= ACC_W4 + 1) ? OFF_W4 + n : -1;       // cols 0,1: h3^T dout_hi + h3^T dout_lo
+          if (dst >= 0 && val != 0.f) atomicAdd(d_params + dst, val);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tbase, 512);
+  if (tid == 0 && *abort_s) atomicExch(status + 2, 1);
+}
+
+int g_num_sms_b = 0;
+int num_sms_b() {
+  if (g_num_sms_b == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms_b, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms_b <= 0) g_num_sms_b = 148;
+  }
+  return g_num_sms_b;
+}
+
+template <int PL>
+int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int Bt, const float* e_saved, const void* acts,
+               void* delta_ws, float* d_params, cudaStream_t st) {
+  int* status = (int*)((uint8_t*)ws + TC_WS_STATUS);
+  const int NT = Bt * (v.n_pad / 128);
+  {
+    BhProfScope ps(BH_CAT_BWD, 1, st);
+    BH_CHECK_CUDA(cudaFuncSetAttribute(tc_dgrad_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SM_TOTAL));
+    int grid = (NT + 1) / 2; if (grid > num_sms_b()) grid = num_sms_b();
+    tc_dgrad_kernel<PL><<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, d_images, Bt, e_saved,
+                                                             (const uint8_t*)acts, (uint8_t*)delta_ws, d_params, status);
+    BH_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    BhProfScope ps(BH_CAT_WGRAD, 1, st);
+    BH_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WCfg<PL>::SM_TOTAL));
+    int grid = NT < num_sms_b() ? NT : num_sms_b();
+    tc_wgrad_kernel<PL><<<grid, kWThreads, WCfg<PL>::SM_TOTAL, st>>>(v.n_pad, Bt, (const uint8_t*)acts, (const uint8_t*)delta_ws,
+                                                             d_params, status);
+    BH_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+size_t bh_tc_delta_bytes_per_frame(int n_pad, int planes) { return tc_delta_bytes_per_frame(n_pad, planes); }
+
+int bh_tc_bwd(const PackedView& v, const void* ws, const float* params, const float* d_images, int Bt,
+              const float* e_saved, const void* acts, void* delta_ws, int planes, float* d_params, cudaStream_t st) {
+  (void)params;
+  if (!e_saved || !acts || !delta_ws) { bh_set_error("bh_tc_bwd: saved e / activations / delta scratch required"); return 1; }
+  return planes == 2 ? launch_bwd<2>(v, ws, d_images, Bt, e_saved, acts, delta_ws, d_params, st)
+                     : launch_bwd<1>(v, ws, d_images, Bt, e_saved, acts, delta_ws, d_params, st);
+}

@@ -21,18 +21,27 @@ __host__ __device__ constexpr uint32_t tc_stage_bytes(int l) { return 2u * tc_pl
 __host__ __device__ constexpr uint32_t tc_stage_off(int l) {                                         // in the weight block
   return l == 0 ? 0u : (l == 1 ? 16384u : (l == 2 ? 81920u : 147456u));
 }
+// Saved activations per frame (bh_tc_fwd with acts), PL = 1 or 2 bf16 planes (hi | hi+lo):
+//   h images    [plane][l=0..3][tile][32 KB]     plane stride n_pad*1024, layer stride n_pad*256
+//   feat images [plane][tile][8 KB] at PL*n_pad*1024 (hi plane: col TC_ONES_COL = 1)
+// Backward scratch per frame: delta images [plane][l][tile][32 KB], then aux images [tile][4 KB]
+// (col 0 = hi, col 1 = lo bf16 part of d loss / d o).
+#define TC_ONES_COL 21
+#define TC_AIMG_BYTES 4096u              // 128 x 16 bf16
+__host__ __device__ inline size_t tc_acts_bytes_per_frame(int n_pad, int PL) { return (size_t)n_pad * (size_t)PL * (1024u + 64u); }
+__host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { return (size_t)n_pad * ((size_t)PL * 1024u + 32u); }
 #define TC_W_BYTES 229376u               // 16K + 64K + 64K + 80K
 #define TC_STAGE_MAX 81920u
 
 // ---- global workspace (bh_tc_ws_bytes) -------------------------------------------------------
 //   [0,256)        int32 status words (0 = ok)
 //   [256,4096)     fp32 constants: b0,b1,b2,b3 (4x128) | W4 (128) | b4 (1)
-//   [4096, +224K)  bf16 weight images, per layer [hi plane | lo plane]
-//   [262144, ...)  backward scratch (per-CTA gradient partials)
+//   [4096, +224K)  fp16 weight images of the forward, per layer [hi plane | lo plane]
+//   [262144,+224K) bf16 weight images of the dgrad chain (cotangents need the fp32 exponent range), same layout
 #define TC_WS_STATUS 0u
 #define TC_WS_CONST 256u
 #define TC_WS_W 4096u
-#define TC_WS_BWD 262144u
+#define TC_WS_WB 262144u
 #define TC_CONST_FLOATS 768              // 641 used
 #define TC_C_B(l) ((l) * 128)
 #define TC_C_W4 512
@@ -70,6 +79,17 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   for (int j = 0; j < 4; ++j) {
     h[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
     l[j] = pack_bf16x2(x[2 * j] - bf16_lo(h[j]), x[2 * j + 1] - bf16_hi(h[j]));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// same split into fp16 planes: 11+11 significand bits, |x - hi - lo| <= max(2^-22 |x|, 2^-25)
+__device__ __forceinline__ void split8_f16(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
+    l[j] = pack_f16x2(x[2 * j] - f16_lo(h[j]), x[2 * j + 1] - f16_hi(h[j]));
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

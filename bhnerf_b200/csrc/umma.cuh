@@ -146,6 +146,34 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Instruction descriptor, kind::f16, fp16 x fp16 -> f32 (a_format = b_format = 0)
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+// ---------------- fp16 helpers ----------------
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {     // lo -> bits [0,16)
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_lo(uint32_t p) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(p));
+  return f;
+}
+__device__ __forceinline__ float f16_hi(uint32_t p) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(p));
+  return f;
+}
+
 // ---------------- bf16 helpers ----------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {    // lo -> bits [0,16)
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -26,7 +26,7 @@ def resolve_impl(impl=None):
     raise ValueError('unknown impl %r' % (impl,))
 
 
-DEFAULT_IMPL = IMPL_SIMT   # switched to IMPL_TC once the tcgen05 family is parity-green on hardware
+DEFAULT_IMPL = IMPL_TC     # tcgen05 family (parity-green on B200); 'simt' selects the fp32 reference kernels
 # cap on the activation workspace of one fused step / backward; more frames than fit are processed in chunks
 DEFAULT_MAX_WORKSPACE = int(float(os.environ.get('BHNERF_MAX_WORKSPACE_GB', '16')) * 2 ** 30)
 

@@ -67,4 +67,9 @@ def run_golden_case(case, impl=None, max_workspace=None):
            'loss_err': abs(float(loss.item()) - float(d['loss'])) / abs(float(d['loss'])),
            'n_active': scene.n_active}
     out.update(extra)
+    g = grads.cpu().numpy().astype(np.float64); gr = d['grads']; o = 0; per = {}
+    for i, (fi, fo) in enumerate([(21, 128), (128, 128), (128, 128), (149, 128), (128, 1)]):
+        for nm, sz in (('W', fi * fo), ('b', fo)):
+            per['%s%d' % (nm, i)] = float(np.abs(g[o:o + sz] - gr[o:o + sz]).max() / np.abs(gr).max()); o += sz
+    out['per_layer'] = per
     return out

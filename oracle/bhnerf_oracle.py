@@ -146,8 +146,13 @@ def velocity_warp_coords(coords, Omega, t_frames, t_start_obs, t_geos, t_injecti
     """bhnerf/emission.py:143-211.  Returns (warped (Bt,...,3) with NaN before injection)."""
     time_dtype = time_dtype or dtype
     coords_t = _t(coords, dtype)
-    t_M = warp_time(t_frames, t_start_obs, t_geos, t_injection, GM_c3, time_dtype)
+    tg = _t(t_geos, time_dtype)
+    if tg.dim() == 0:                                              # scalar t_geos broadcasts like Omega (:196-200)
+        tg = tg.reshape((1,) * (coords_t.dim() - 1))
+    t_M = warp_time(t_frames, t_start_obs, tg, t_injection, GM_c3, time_dtype)
     Om = _t(Omega, time_dtype)
+    if Om.dim() == 0:                                              # emission.py:190-191: scalar Omega
+        Om = Om.reshape((1,) * (coords_t.dim() - 1))
     theta = (t_M * Om)                                            # emission.py:204
     theta = torch.where(t_M < 0.0, torch.full_like(theta, float('nan')), theta)  # :205
     theta = theta.to(dtype)

@@ -111,7 +111,7 @@ def run_reference(args):
         return
     from bhnerf_b200 import synthetic
     c = synthetic.CONFIGS[args.workload]
-    nfr = args.cpu_frames or 2
+    nfr = args.cpu_frames or 4
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_leg(args.workload, 1)
     vals, secs = [], []
@@ -257,21 +257,28 @@ def main():
         # dominant kernel = the category with the most device time
         names = ['render_fwd', 'render_bwd', 'wgrad', 'heads', 'misc']
         ms_by = {n: cat_ms[i] for i, n in enumerate(names)}
-        flops_by = {'render_fwd': FLOP_FWD, 'render_bwd': FLOP_BWD if impl == engine.IMPL_TC else 49280 * 2,
-                    'wgrad': 54656 * 2}
+        flops_by = {'render_fwd': FLOP_FWD, 'render_bwd': 49280 * 2, 'wgrad': 54656 * 2}   # fwd | dgrad chain | wgrad
         dom = max(flops_by, key=lambda n: ms_by[n])
         launches_dom = max(int(cat_sc[names.index(dom)]), 1)
         per_launch_s = ms_by[dom] * 1e-3 / launches_dom
         eval_per_launch = eval_per_step * args.steps / launches_dom
         achieved = eval_per_launch * flops_by[dom] / per_launch_s / 1e12 if per_launch_s > 0 else 0.0
+        # DRAM bytes per launch of the dominant kernel: per-sample figure of the committed ncu --set full capture
+        # (profiles/ncu_traffic.json) x the evaluated samples of one launch
+        traffic = None
+        try:
+            per_sample = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))[dom + '_' + impl_name]
+            traffic = per_sample['dram_bytes_per_eval_sample'] * eval_per_launch
+        except Exception:
+            pass
         roofline = {'bound': 'tensor', 'kernel': dom + '_' + impl_name, 'achieved': achieved, 'peak': tensor_peak,
-                    'unit': 'TFLOP/s', 'frac': achieved / tensor_peak, 'traffic': None, 'peak_source': peak_src,
+                    'unit': 'TFLOP/s', 'frac': achieved / tensor_peak, 'traffic': traffic, 'peak_source': peak_src,
                     'avg_launch_ms': per_launch_s * 1e3, 'algorithmic_flop_per_sample': flops_by[dom],
                     'kernel_ms_per_step': {n: ms_by[n] / args.steps for n in names},
                     'step_algorithmic_tflops': eval_per_step * (FLOP_FWD + FLOP_BWD) * args.steps / (ms * 1e-3) / 1e12}
         cpu = None
         if not args.no_cpu_baseline:
-            nfr = args.cpu_frames or 2
+            nfr = args.cpu_frames or 8
             v, dt, cores = cpu_reference_leg(args.workload, nfr)
             cpu = {'value': v, 'unit': 'dense samples/s', 'cores': cores, 'kind': 'port',
                    'sample': '%d of %d frames (%.1f s), float32 dense torch-CPU restatement of the reference JAX path'
@@ -280,7 +287,7 @@ def main():
             'metric': 'geodesic samples/s, fwd+bwd train step', 'value': value, 'unit': 'dense samples/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16x3 split operands, f32 accumulate (tcgen05)' if impl == engine.IMPL_TC else 'f32 (FFMA)',
+            'dtype': 'f16x3 (fwd) / bf16 (bwd) split operands, f32 accumulate (tcgen05)' if impl == engine.IMPL_TC else 'f32 (FFMA)',
             'data': 'synthetic',
             'config': {'workload': args.workload, 'rays': P, 'samples_per_ray': Gs, 'frames_per_gpu': Bt,
                        'stokes': S, 'loss': kind, 'mlp': '4x128 relu + skip, posenc deg 3', 'kernels': impl_name,

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libbhnerf_b200.so')
+LIB_PATH = os.environ.get('BHNERF_B200_LIB', os.path.join(_HERE, 'lib', 'libbhnerf_b200.so'))   # override: instrumented builds
 
 IMPL_SIMT, IMPL_TC = 0, 1
 LOSS_FULL, LOSS_LC, LOSS_VIS, LOSS_AMP, LOSS_CPHASE = 0, 1, 2, 3, 4

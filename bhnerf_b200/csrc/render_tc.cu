@@ -13,14 +13,32 @@
 // D (fp32) is read from TMEM with tcgen05.ld and the next layer's A operand is written back to TMEM with
 // tcgen05.st (TS-form MMA); only the 21 posenc features go through shared memory (SS-form, K-major).
 #include <cuda_fp16.h>
+#include <type_traits>
 #include <stdlib.h>
 #include "tc_common.cuh"
 
 using namespace tc;
 
+// Optional cycle accounting (-DBH_TC_TIMING): block 0 writes, per role, the cycles spent waiting vs working into
+// the workspace status words [8..20) (two int32 per counter).  Compiled out by default.
+#ifdef BH_TC_TIMING
+#define BH_TIMING_DECL(v) long long v = 0; long long _t0_##v = 0; (void)_t0_##v;
+#define BH_TIMING_BEGIN _bh_t0 = clock64();
+#define BH_TIMING_END(v) v += clock64() - _bh_t0;
+#define BH_TIMING_T0 long long _bh_t0 = 0;
+#define BH_TIMING_STORE(st, i, v) if (blockIdx.x == 0) { (st)[i] = (int)(v & 0xffffffffll); (st)[(i) + 1] = (int)(v >> 32); }
+#else
+#define BH_TIMING_T0
+#define BH_TIMING_DECL(v)
+#define BH_TIMING_BEGIN
+#define BH_TIMING_END(v)
+#define BH_TIMING_STORE(st, i, v)
+#endif
+
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 576;            // 16 epilogue warps + MMA issuer + weight producer
+constexpr int kMmaWarp = 16;
 constexpr uint32_t SM_WSTAGE = 0;                                  // 2 x 80 KB weight ring
 constexpr uint32_t SM_FEAT = 2 * TC_STAGE_MAX;                     // 2 slots x [hi 8K | lo 8K]
 constexpr uint32_t SM_CONST = SM_FEAT + 2 * 2 * TC_FIMG_BYTES;     // 768 floats
@@ -70,35 +88,95 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ params, uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// MMA issue for one (layer, slot): D[128x128] = A[128xK] * W_l[Kx128], NPASS bf16 products
+// MMA issue for one (layer, slot): D[128x128] = A[128xK] * W_l[Kx128], NPASS fp16 products
 //   pass 0: a_hi*w_hi   pass 1: a_lo*w_hi   pass 2: a_hi*w_lo
+// Called by ONE elected lane; fully unrolled with the descriptor halves precomputed, so each tcgen05.mma costs a
+// 32-bit add instead of a descriptor rebuild (measured: 74 instead of 135 cycles per MMA, scripts/run_umma_bench.py).
 // ------------------------------------------------------------------------------------------------
-template <int NPASS>
-__device__ __forceinline__ void issue_layer(int l, uint32_t tmem_d, uint32_t tmem_a, uint32_t feat_smem,
-                                            uint32_t w_smem, uint32_t idesc) {
-  const uint32_t K = tc_layer_K(l), plane = tc_plane_bytes(l), w_cs = (K / 8) * 128u;
-  const int nks = (int)(K / 16);
-  uint32_t acc = 0;
-#pragma unroll 1
+template <int NPASS, int L>
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t tmem_a, uint32_t feat_smem, uint32_t w_smem,
+                                            uint32_t idesc) {
+  constexpr uint32_t K = tc_layer_K(L), plane = tc_plane_bytes(L), w_cs = (K / 8) * 128u;
+  constexpr int nks = (int)(K / 16);
+  // B: image [k][n] read MN-major: K groups advance by RS (LBO), N groups by CS (SBO)
+  const uint32_t b_hi = desc_hi(w_cs);
+  const uint32_t b_lo[2] = {desc_lo(w_smem, TC_IMG_RS), desc_lo(w_smem + plane, TC_IMG_RS)};
+  // A (features): image [s][k] read K-major: K groups advance by CS (LBO), M groups by RS (SBO)
+  const uint32_t a_hi = desc_hi(TC_IMG_RS);
+  const uint32_t a_lo[2] = {desc_lo(feat_smem, TC_SIMG_CS), desc_lo(feat_smem + TC_FIMG_BYTES, TC_SIMG_CS)};
+#pragma unroll
   for (int pass = 0; pass < NPASS; ++pass) {
-    const uint32_t a_lo = (pass == 1) ? 1u : 0u, w_lo = (pass == 2) ? 1u : 0u;
-#pragma unroll 1
+    const int ap = (pass == 1) ? 1 : 0, wp = (pass == 2) ? 1 : 0;
+#pragma unroll
     for (int ks = 0; ks < nks; ++ks) {
-      // B: image [k][n] read MN-major: K groups advance by RS (LBO), N groups by CS (SBO)
-      uint64_t bd = make_desc(w_smem + w_lo * plane + (uint32_t)ks * 2u * TC_IMG_RS, TC_IMG_RS, w_cs);
-      const bool a_from_smem = (l == 0) || (l == 3 && ks >= 8);
-      if (a_from_smem) {
-        // A: feature image [s][k] read K-major: K groups advance by CS (LBO), M groups by RS (SBO)
-        uint32_t kk = (l == 0) ? (uint32_t)ks : (uint32_t)(ks - 8);
-        uint64_t ad = make_desc(feat_smem + a_lo * TC_FIMG_BYTES + kk * 2u * TC_SIMG_CS, TC_SIMG_CS, TC_IMG_RS);
-        mma_ss(tmem_d, ad, bd, idesc, acc);
+      const uint32_t bl = b_lo[wp] + (uint32_t)ks * ((2u * TC_IMG_RS) >> 4);
+      const uint32_t acc = (pass | ks) ? 1u : 0u;
+      if (L == 0 || (L == 3 && ks >= 8)) {
+        const int kk = (L == 0) ? ks : ks - 8;
+        mma_ss_raw(tmem_d, a_lo[ap] + (uint32_t)kk * ((2u * TC_SIMG_CS) >> 4), a_hi, bl, b_hi, idesc, acc);
       } else {
-        mma_ts(tmem_d, tmem_a + a_lo * 64u + (uint32_t)ks * 8u, bd, idesc, acc);
+        mma_ts_raw(tmem_d, tmem_a + (uint32_t)ap * 64u + (uint32_t)ks * 8u, bl, b_hi, idesc, acc);
       }
-      acc = 1;
     }
   }
 }
+
+// ---- branch-free sine of the reference's reduced argument r in [0, 2*100pi) (safe_sin, network.py:16) ----
+// Cody-Waite reduction by pi/2 (3 constants, j*C1 exact for j < 2^16) + the two minimax polynomials on
+// [-pi/4, pi/4]; abs error ~1e-7 like sinf(), but no slow-path branch, so the nine sines of a thread interleave.
+__device__ __forceinline__ float sin_reduced(float r) {
+  const float j = rintf(r * 0.636619772367581343f);
+  const int q = (int)j;
+  float x = fmaf(-j, 1.5703125f, r);
+  x = fmaf(-j, 4.837512969970703125e-4f, x);
+  x = fmaf(-j, 7.54978995489188216e-8f, x);
+  const float x2 = x * x;
+  const float sn = fmaf(fmaf(fmaf(-1.9515295891e-4f, x2, 8.3321608736e-3f), x2, -1.6666654611e-1f), x2 * x, x);
+  const float cs = fmaf(fmaf(fmaf(2.443315711809948e-5f, x2, -1.388731625493765e-3f), x2, 4.166664568298827e-2f),
+                        x2 * x2, fmaf(-0.5f, x2, 1.0f));
+  const float val = (q & 1) ? cs : sn;
+  return (q & 2) ? -val : val;
+}
+__device__ __forceinline__ float safe_sin_fast(float a) {      // same float32 ARGUMENT arithmetic as bh_safe_sin
+  float r = (fabsf(a) < BH_100PI_F) ? a : fmodf(a, BH_100PI_F);
+  if (r < 0.0f) r = __fadd_rn(r, BH_100PI_F);
+  return sin_reduced(r);
+}
+
+// warped + scaled coordinates of one sample (bh_features without the encodings)
+__device__ __forceinline__ bool warp_coords(float x, float y, float z, float om, float tg, float tfc,
+                                            const FrameConsts& fc, float* u) {
+  float tM = __fsub_rn(__fadd_rn(tfc, tg), fc.t_injection);
+  bool valid = !(tM < 0.0f);
+  float sn, cs;
+  sincosf(__fmul_rn(tM, om), &sn, &cs);
+  u[0] = __fdiv_rn(x * cs + y * sn, fc.scale);
+  u[1] = __fdiv_rn(y * cs - x * sn, fc.scale);
+  u[2] = __fdiv_rn(z, fc.scale);
+  if (!valid) { u[0] = 0.f; u[1] = 0.f; u[2] = 0.f; }
+  return valid;
+}
+
+// hi = x rounded toward zero with the ReLU folded in (so lo = x - hi >= 0 wherever x > 0 and the second
+// relu-conversion is exact for x <= 0): 8 instructions per pair instead of 10
+__device__ __forceinline__ uint32_t pack_f16x2_rz_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_rn_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+constexpr uint32_t SM_PART = SM_BARS + 128;                        // [slot][row] partial of the last layer
+constexpr uint32_t SM_TOTAL2 = SM_PART + 2 * 128 * 4;
 
 template <int NPASS, int SAVE>      // SAVE = bf16 planes of every activation kept for the backward (0, 1, 2)
 __global__ void __launch_bounds__(kThreads, 1)
@@ -111,6 +189,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
   uint64_t* bars = (uint64_t*)(smem + SM_BARS);
   uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
   int* abort_s = (int*)(tmem_base_s + 1);
+  float* part = (float*)(smem + SM_PART);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_per_frame = v.n_pad / 128;
   const int NT = Bt * tiles_per_frame;
@@ -119,19 +198,21 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
   if (tid == 0) {
     mbar_init(&bars[BAR_WFULL + 0], 1); mbar_init(&bars[BAR_WFULL + 1], 1);
     mbar_init(&bars[BAR_WEMPTY + 0], 1); mbar_init(&bars[BAR_WEMPTY + 1], 1);
-    mbar_init(&bars[BAR_AREADY + 0], 4); mbar_init(&bars[BAR_AREADY + 1], 4);
+    mbar_init(&bars[BAR_AREADY + 0], 8); mbar_init(&bars[BAR_AREADY + 1], 8);
     mbar_init(&bars[BAR_DREADY + 0], 1); mbar_init(&bars[BAR_DREADY + 1], 1);
     abort_s[0] = 0; abort_s[1] = 0;
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(tmem_base_s, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_base_s, 512);
   for (int i = tid; i < TC_CONST_FLOATS; i += kThreads) cst[i] = ((const float*)(ws + TC_WS_CONST))[i];
+  for (int i = tid; i < (int)(2 * 2 * TC_FIMG_BYTES / 16); i += kThreads)      // feature columns 24..31 stay zero
+    reinterpret_cast<uint4*>(featimg)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tbase = *tmem_base_s;
 
-  if (warp == 9) {
+  if (warp == kMmaWarp + 1) {
     // ===================== weight producer =====================
     if (lane == 0) {
       uint32_t wcnt = 0;
@@ -150,43 +231,74 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer: the whole warp runs the control flow, one elected lane issues =====================
+    {
       const uint32_t idesc = make_idesc_f16(128, 128, 0, 1);
       uint32_t wcnt = 0, a_phase[2] = {0u, 0u};
-      for (int r = 0;; ++r) {
+      BH_TIMING_T0 BH_TIMING_DECL(t_ww) BH_TIMING_DECL(t_wa) BH_TIMING_DECL(t_is)
+      bool ok = true;
+      auto layer_step = [&](auto Ltag, int T0) {
+        constexpr int L = decltype(Ltag)::value;
+        uint32_t st = wcnt & 1u;
+        BH_TIMING_BEGIN
+        ok = ok && wait(&bars[BAR_WFULL + st], (wcnt >> 1) & 1u, ab);
+        BH_TIMING_END(t_ww)
+        for (int s = 0; s < 2 && ok; ++s) {
+          if (T0 + s >= NT) continue;
+          BH_TIMING_BEGIN
+          ok = wait(&bars[BAR_AREADY + s], a_phase[s], ab);
+          BH_TIMING_END(t_wa)
+          if (!ok) break;
+          a_phase[s] ^= 1u;
+          tc_fence_after_sync();
+          BH_TIMING_BEGIN
+          if (elect_one()) {
+            issue_layer<NPASS, L>(tbase + (uint32_t)s * 256u, tbase + (uint32_t)s * 256u + 128u,
+                                  smem_u32(featimg + s * 2 * TC_FIMG_BYTES), smem_u32(wst + st * TC_STAGE_MAX), idesc);
+            mma_commit_raw(&bars[BAR_DREADY + s]);
+          }
+          __syncwarp();
+          BH_TIMING_END(t_is)
+        }
+        if (ok) {
+          if (elect_one()) mma_commit_raw(&bars[BAR_WEMPTY + st]);
+          __syncwarp();
+        }
+        ++wcnt;
+      };
+      for (int r = 0; ok; ++r) {
         int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
         if (T0 >= NT) break;
-        bool ok = true;
-        for (int l = 0; l < 4 && ok; ++l, ++wcnt) {
-          uint32_t st = wcnt & 1u;
-          ok = wait(&bars[BAR_WFULL + st], (wcnt >> 1) & 1u, ab);
-          if (!ok) break;
-          for (int s = 0; s < 2; ++s) {
-            if (T0 + s >= NT) continue;
-            ok = wait(&bars[BAR_AREADY + s], a_phase[s], ab);
-            if (!ok) break;
-            a_phase[s] ^= 1u;
-            tc_fence_after_sync();
-            issue_layer<NPASS>(l, tbase + (uint32_t)s * 256u, tbase + (uint32_t)s * 256u + 128u,
-                               smem_u32(featimg + s * 2 * TC_FIMG_BYTES), smem_u32(wst + st * TC_STAGE_MAX), idesc);
-            mma_commit(&bars[BAR_DREADY + s]);
-          }
-          if (!ok) break;
-          mma_commit(&bars[BAR_WEMPTY + st]);
-        }
-        if (!ok) break;
+        layer_step(std::integral_constant<int, 0>{}, T0);
+        layer_step(std::integral_constant<int, 1>{}, T0);
+        layer_step(std::integral_constant<int, 2>{}, T0);
+        layer_step(std::integral_constant<int, 3>{}, T0);
       }
+      if (lane == 0) { BH_TIMING_STORE(status, 8, t_ww) BH_TIMING_STORE(status, 10, t_wa) BH_TIMING_STORE(status, 12, t_is) }
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps =====================
-    const int slot = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    // ===================== epilogue warps: (slot, column half, lane quadrant) =====================
+    const int slot = warp >> 3, half = (warp >> 2) & 1, q = warp & 3, row = q * 32 + lane;
     const uint32_t t_lane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 256u;
     uint8_t* my_feat = featimg + slot * 2 * TC_FIMG_BYTES;
+    const uint32_t pair_bar = 1u + (uint32_t)(slot * 4 + q);          // named barrier of the two warps of a row
     uint32_t d_phase = 0;
     bool ok = true;
+    // inputs of the first tile; later tiles are prefetched one round ahead
+    float in_x = 0.f, in_y = 0.f, in_z = 0.f, in_om = 0.f, in_tg = 0.f, in_tf = 0.f;
+    int in_ray = -1;
+    auto load_inputs = [&](int r) {
+      int T = (r * (int)gridDim.x + (int)blockIdx.x) * 2 + slot;
+      if (T < NT) {
+        const int b = T / tiles_per_frame, i = (T - b * tiles_per_frame) * 128 + row;
+        in_x = v.x[i]; in_y = v.y[i]; in_z = v.z[i]; in_om = v.omega[i]; in_tg = v.tgeo[i];
+        in_tf = t_frames[b]; in_ray = v.ray[i];
+      }
+    };
+    load_inputs(0);
+    BH_TIMING_T0 BH_TIMING_DECL(t_ft) BH_TIMING_DECL(t_wd) BH_TIMING_DECL(t_ep)
     for (int r = 0; ok; ++r) {
       int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
       if (T0 >= NT) break;
@@ -194,68 +306,124 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
       if (T >= NT) continue;
       const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
       const int i = tile * 128 + row;
-      // ---- warp + posenc in registers, split into bf16 hi/lo feature images ----
-      float f[32];
-      const float tfc = bh_frame_time(t_frames[b], fc);
-      const bool valid = bh_features(v.x[i], v.y[i], v.z[i], v.omega[i], v.tgeo[i], tfc, fc, f);
-#pragma unroll
-      for (int k = BH_NF; k < 32; ++k) f[k] = 0.f;
-      // column 21 = 1: the weight images have zero rows there, and the wgrad kernel reads bias gradients off it
-      if (SAVE) f[TC_ONES_COL] = 1.f;
+      // ---- warp + posenc in registers: half 0 writes u and the sines (cols 0..11), half 1 the cosines (12..20) ----
+      BH_TIMING_BEGIN
+      float u[3];
+      const bool valid = warp_coords(in_x, in_y, in_z, in_om, in_tg, bh_frame_time(in_tf, fc), fc, u);
+      const int ray = in_ray;
+      load_inputs(r + 1);
       uint8_t* feat_save = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) +
                                       (size_t)v.n_pad * 1024u * SAVE + (size_t)tile * TC_FIMG_BYTES : nullptr;
+      {
+        float f[16];
+        if (half == 0) {
+          f[0] = u[0]; f[1] = u[1]; f[2] = u[2];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 hi, lo;
-        split8_f16(f + 8 * g, hi, lo);
-        uint32_t off = sample_img_off(row, g);
-        *reinterpret_cast<uint4*>(my_feat + off) = hi;
-        if (NPASS > 1) *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + off) = lo;
+          for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[3 + 3 * ii + c] = safe_sin_fast(u[c] * (float)(1 << ii));
+          f[12] = f[13] = f[14] = f[15] = 0.f;
+        } else {
+#pragma unroll
+          for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              f[4 + 3 * ii + c] = safe_sin_fast(__fadd_rn(u[c] * (float)(1 << ii), BH_HALFPI_F));     // cols 12..20
+          f[0] = f[1] = f[2] = f[3] = 0.f;
+          f[13] = SAVE ? 1.f : 0.f;      // col 21 = 1: zero weight rows there; wgrad reads bias gradients off it
+          f[14] = f[15] = 0.f;
+        }
+        // half 0: chunk 0 (cols 0..7) + first 8 bytes of chunk 1 (cols 8..11)
+        // half 1: last 8 bytes of chunk 1 (cols 12..15) + chunk 2 (cols 16..23) [+ zero chunk 3 of the saved copy]
+        uint4 hA, lA, hB, lB;
+        split8_f16(f, hA, lA);
+        split8_f16(f + 8, hB, lB);
+        const uint32_t o0 = sample_img_off(row, 0), o1 = sample_img_off(row, 1), o2 = sample_img_off(row, 2);
+        if (half == 0) {
+          *reinterpret_cast<uint4*>(my_feat + o0) = hA;
+          *reinterpret_cast<uint2*>(my_feat + o1) = make_uint2(hB.x, hB.y);
+          if (NPASS > 1) {
+            *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + o0) = lA;
+            *reinterpret_cast<uint2*>(my_feat + TC_FIMG_BYTES + o1) = make_uint2(lB.x, lB.y);
+          }
+        } else {
+          *reinterpret_cast<uint2*>(my_feat + o1 + 8) = make_uint2(hA.z, hA.w);
+          *reinterpret_cast<uint4*>(my_feat + o2) = hB;
+          if (NPASS > 1) {
+            *reinterpret_cast<uint2*>(my_feat + TC_FIMG_BYTES + o1 + 8) = make_uint2(lA.z, lA.w);
+            *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + o2) = lB;
+          }
+        }
         if (SAVE) {                                     // the backward's operands are bf16 (range of the cotangents)
-          split8(f + 8 * g, hi, lo);
-          *reinterpret_cast<uint4*>(feat_save + off) = hi;
-          if (SAVE == 2) *reinterpret_cast<uint4*>(feat_save + (size_t)v.n_pad * 64u + off) = lo;
+          split8(f, hA, lA);
+          split8(f + 8, hB, lB);
+          const size_t lo_off = (size_t)v.n_pad * 64u;
+          if (half == 0) {
+            *reinterpret_cast<uint4*>(feat_save + o0) = hA;
+            *reinterpret_cast<uint2*>(feat_save + o1) = make_uint2(hB.x, hB.y);
+            if (SAVE == 2) {
+              *reinterpret_cast<uint4*>(feat_save + lo_off + o0) = lA;
+              *reinterpret_cast<uint2*>(feat_save + lo_off + o1) = make_uint2(lB.x, lB.y);
+            }
+          } else {
+            *reinterpret_cast<uint2*>(feat_save + o1 + 8) = make_uint2(hA.z, hA.w);
+            *reinterpret_cast<uint4*>(feat_save + o2) = hB;
+            *reinterpret_cast<uint4*>(feat_save + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
+            if (SAVE == 2) {
+              *reinterpret_cast<uint2*>(feat_save + lo_off + o1 + 8) = make_uint2(lA.z, lA.w);
+              *reinterpret_cast<uint4*>(feat_save + lo_off + o2) = lB;
+              *reinterpret_cast<uint4*>(feat_save + lo_off + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_AREADY + slot]);
+      BH_TIMING_END(t_ft)
       uint8_t* act_tile = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + (size_t)tile * TC_SIMG_BYTES : nullptr;
-      float o = cst[TC_C_B4];
+      float o = 0.f;
       for (int l = 0; l < 4; ++l) {
+        BH_TIMING_BEGIN
         ok = wait(&bars[BAR_DREADY + slot], d_phase, ab);
+        BH_TIMING_END(t_wd)
         if (!ok) break;
         d_phase ^= 1u;
         tc_fence_after_sync();
-        const float* bias = cst + TC_C_B(l);
+        BH_TIMING_BEGIN
         uint8_t* act_img = SAVE ? act_tile + (size_t)l * ((size_t)v.n_pad * 256u) : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(t_lane + (uint32_t)c0, raw);
-          tmem_wait_ld();
+        // this warp's 64 columns: both TMEM loads in flight before the first use
+        uint32_t raw[2][32];
+        tmem_ld32(t_lane + (uint32_t)(half * 64), raw[0]);
+        tmem_ld32(t_lane + (uint32_t)(half * 64 + 32), raw[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = half * 64 + cc * 32;
+          const float* bias = cst + TC_C_B(l) + c0;
           float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(raw[j]) + bias[c0 + j], 0.f);
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(raw[cc][j]) + bias[j];        // pre-activation
           uint32_t hi[16], lo[16];
           if (l < 3) {                                  // next layer's A operand: fp16 hi/lo planes in TMEM
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              hi[j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
-              if (NPASS > 1) lo[j] = pack_f16x2(x[2 * j] - f16_lo(hi[j]), x[2 * j + 1] - f16_hi(hi[j]));
+              hi[j] = pack_f16x2_rz_relu(x[2 * j], x[2 * j + 1]);
+              if (NPASS > 1) lo[j] = pack_f16x2_rn_relu(x[2 * j] - f16_lo(hi[j]), x[2 * j + 1] - f16_hi(hi[j]));
             }
             tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), hi);
             if (NPASS > 1) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), lo);
           } else {
             const float* w4 = cst + TC_C_W4 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o = fmaf(x[j], w4[j], o);
+            for (int j = 0; j < 32; ++j) o = fmaf(fmaxf(x[j], 0.f), w4[j], o);
           }
-          if (SAVE) {                                   // saved for the backward as bf16 planes
+          if (SAVE) {                                   // saved for the backward as bf16 planes (ReLU folded into the cvt)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              hi[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-              if (SAVE == 2) lo[j] = pack_bf16x2(x[2 * j] - bf16_lo(hi[j]), x[2 * j + 1] - bf16_hi(hi[j]));
+              hi[j] = pack_bf16x2_rn_relu(x[2 * j], x[2 * j + 1]);
+              if (SAVE == 2)
+                lo[j] = pack_bf16x2(fmaxf(x[2 * j], 0.f) - bf16_lo(hi[j]), fmaxf(x[2 * j + 1], 0.f) - bf16_hi(hi[j]));
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -273,16 +441,26 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[BAR_AREADY + slot]);
         }
+        BH_TIMING_END(t_ep)
       }
       if (!ok) break;
-      float e = bh_sigmoid_m10(o);
-      if (!(fabsf(o) <= 3.0e38f)) abort_s[1] = 1;      // fp16 operand overflow (|activation| > 65504): flag, do not hide
-      e_out[(size_t)b * v.n_pad + i] = (valid && v.ray[i] >= 0) ? e : 0.f;     // network.py:232
+      // last layer: the two halves of a row combine their partial dot products through shared memory
+      if (half == 1) {
+        part[slot * 128 + row] = o;
+        asm volatile("bar.arrive %0, 64;" ::"r"(pair_bar) : "memory");
+      } else {
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        o += part[slot * 128 + row] + cst[TC_C_B4];
+        float e = bh_sigmoid_m10(o);
+        if (!(fabsf(o) <= 3.0e38f)) abort_s[1] = 1;    // fp16 operand overflow (|activation| > 65504): flag, do not hide
+        e_out[(size_t)b * v.n_pad + i] = (valid && ray >= 0) ? e : 0.f;       // network.py:232
+      }
     }
+    if (tid == 0) { BH_TIMING_STORE(status, 14, t_ft) BH_TIMING_STORE(status, 16, t_wd) BH_TIMING_STORE(status, 18, t_ep) }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tbase, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tbase, 512);
   if (tid == 0 && *abort_s) atomicExch(status, 1);
   if (tid == 0 && abort_s[1]) atomicExch(status + 3, 1);
 }
@@ -301,10 +479,10 @@ template <int NPASS, int SAVE>
 int launch_fwd(const PackedView& v, const FrameConsts& fc, const void* ws, const float* t_frames, int Bt,
                float* e_out, void* acts, cudaStream_t st) {
   auto kern = tc_fwd_kernel<NPASS, SAVE>;
-  BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL2));
   int NT = Bt * (v.n_pad / 128);
   int grid = (NT + 1) / 2; if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, kThreads, SM_TOTAL, st>>>(v, fc, (const uint8_t*)ws, t_frames, Bt, e_out, (uint8_t*)acts,
+  kern<<<grid, kThreads, SM_TOTAL2, st>>>(v, fc, (const uint8_t*)ws, t_frames, Bt, e_out, (uint8_t*)acts,
                                         (int*)((uint8_t*)ws + TC_WS_STATUS));
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -79,7 +79,7 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
     }
     __syncwarp();
   } else if (warp == 8) {
-    if (lane == 0) {
+    {   // whole warp runs the loop; elect.sync inside the issue wrappers picks the issuing lane
       const uint32_t idesc = make_idesc(128, 128, 0, 0);      // A from TMEM, B K-major
       uint32_t a_phase[2] = {0u, 0u};
       bool ok = wait(&bars[DB_WFULL], 0, ab);
@@ -96,18 +96,20 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
             a_phase[s] ^= 1u;
             tc_fence_after_sync();
             const uint32_t td = tbase + (uint32_t)s * 256u, ta = td + 128u;
-            uint32_t acc = 0;
-            // passes: d_hi*W_hi, d_hi*W_lo, and with both planes d_lo*W_hi
-#pragma unroll 1
-            for (uint32_t p = 0; p < (PL == 2 ? 3u : 2u); ++p)
-#pragma unroll 1
-              for (uint32_t ks = 0; ks < 8; ++ks) {
-                // B' [K'=n][N'=k] = W_l[k][n]: the forward image read K-major (K' groups = column groups)
-                uint64_t bd = make_desc(wl + (p == 1 ? plane : 0u) + ks * 2u * cs, cs, TC_IMG_RS);
-                mma_ts(td, ta + (p == 2 ? 64u : 0u) + ks * 8u, bd, idesc, acc);
-                acc = 1;
-              }
-            mma_commit(&bars[DB_DREADY + s]);
+            if (elect_one()) {
+              // B' [K'=n][N'=k] = W_l[k][n]: the forward-layout image read K-major (K' groups = column groups);
+              // passes: d_hi*W_hi, d_hi*W_lo, and with both planes d_lo*W_hi.  Unrolled, descriptor halves precomputed.
+              const uint32_t b_hi = desc_hi(TC_IMG_RS), b_lo0 = desc_lo(wl, cs), b_lo1 = desc_lo(wl + plane, cs);
+              const uint32_t kstep = (2u * cs) >> 4;
+#pragma unroll
+              for (int pp = 0; pp < (PL == 2 ? 3 : 2); ++pp)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  mma_ts_raw(td, ta + (pp == 2 ? 64u : 0u) + (uint32_t)ks * 8u, (pp == 1 ? b_lo1 : b_lo0) + (uint32_t)ks * kstep,
+                             b_hi, idesc, (pp | ks) ? 1u : 0u);
+              mma_commit_raw(&bars[DB_DREADY + s]);
+            }
+            __syncwarp();
           }
         }
       }
@@ -319,14 +321,13 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
     }
     __syncwarp();
   } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, elect.sync inside the issue wrappers) =====================
+    {
       const uint32_t id128 = make_idesc(128, 128, 1, 1), id32 = make_idesc(128, 32, 1, 1), id16 = make_idesc(128, 16, 1, 1);
       uint32_t cnt = 0, fcnt = 0;
       bool ok = true;
       uint32_t later_tile = 0;               // 0 for the CTA's first tile: accumulators start from zero
       // all operands are [s][c] images read MN-major: K (= sample) groups advance by RS, M/N groups by CS
-      auto desc = [](uint32_t base, uint32_t ks) { return make_desc(base + ks * 2u * TC_IMG_RS, TC_IMG_RS, TC_SIMG_CS); };
       for (int T = blockIdx.x; T < NT && ok; T += gridDim.x, ++fcnt, later_tile = 1) {
         uint32_t fs = fcnt & 1u;
         ok = wait(&bars[WB_FFULL + fs], (fcnt >> 1) & 1u, ab);
@@ -343,30 +344,38 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
           const uint32_t A = smem_u32(smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES), B = A + TC_SIMG_BYTES;
           const uint32_t feat = fbuf + (uint32_t)pb * TC_FIMG_BYTES;
           const uint32_t started = later_tile | ((pa | pb) ? 1u : 0u);     // (hi,hi) is each accumulator's first product
-#pragma unroll 1
-          for (uint32_t ks = 0; ks < 8; ++ks) {
-            const uint32_t acc = started | (ks > 0 ? 1u : 0u);
-            const uint64_t ad = desc(A, ks);
-            if (j == 0) {
-              mma_ss(tbase + ACC_W3, ad, desc(B, ks), id128, acc);
-              mma_ss(tbase + ACC_W3F, ad, desc(feat, ks), id32, acc);
-            } else if (j == 1) {
-              mma_ss(tbase + ACC_W2, ad, desc(B, ks), id128, acc);
-              if (pb == 0) mma_ss(tbase + ACC_B2, ad, desc(fbuf + 2u * TC_SIMG_CS, ks), id16, acc);
-            } else if (j == 2) {
-              mma_ss(tbase + ACC_W1, ad, desc(B, ks), id128, acc);
-              if (pb == 0) mma_ss(tbase + ACC_B1, ad, desc(fbuf + 2u * TC_SIMG_CS, ks), id16, acc);
-            } else if (j == 3) {
-              mma_ss(tbase + ACC_W0F, ad, desc(feat, ks), id32, acc);
-            } else {
-              mma_ss(tbase + ACC_W4, ad, desc(aux, ks), id16, acc);
+          if (elect_one()) {
+            // all operands are [s][c] images read MN-major: K (= sample) groups advance by RS (LBO), M/N groups by CS (SBO)
+            const uint32_t hi = desc_hi(TC_SIMG_CS), kstep = (2u * TC_IMG_RS) >> 4;
+            const uint32_t a_lo = desc_lo(A, TC_IMG_RS), b_lo = desc_lo(B, TC_IMG_RS), f_lo = desc_lo(feat, TC_IMG_RS);
+            const uint32_t o_lo = desc_lo(fbuf + 2u * TC_SIMG_CS, TC_IMG_RS), x_lo = desc_lo(aux, TC_IMG_RS);
+#pragma unroll
+            for (uint32_t ks = 0; ks < 8; ++ks) {
+              const uint32_t acc = started | (ks > 0 ? 1u : 0u);
+              const uint32_t al = a_lo + ks * kstep;
+              if (j == 0) {
+                mma_ss_raw(tbase + ACC_W3, al, hi, b_lo + ks * kstep, hi, id128, acc);
+                mma_ss_raw(tbase + ACC_W3F, al, hi, f_lo + ks * kstep, hi, id32, acc);
+              } else if (j == 1) {
+                mma_ss_raw(tbase + ACC_W2, al, hi, b_lo + ks * kstep, hi, id128, acc);
+                if (pb == 0) mma_ss_raw(tbase + ACC_B2, al, hi, o_lo + ks * kstep, hi, id16, acc);
+              } else if (j == 2) {
+                mma_ss_raw(tbase + ACC_W1, al, hi, b_lo + ks * kstep, hi, id128, acc);
+                if (pb == 0) mma_ss_raw(tbase + ACC_B1, al, hi, o_lo + ks * kstep, hi, id16, acc);
+              } else if (j == 3) {
+                mma_ss_raw(tbase + ACC_W0F, al, hi, f_lo + ks * kstep, hi, id32, acc);
+              } else {
+                mma_ss_raw(tbase + ACC_W4, al, hi, x_lo + ks * kstep, hi, id16, acc);
+              }
             }
+            mma_commit_raw(&bars[WB_EMPTY + st]);
           }
-          mma_commit(&bars[WB_EMPTY + st]);
+          __syncwarp();
         }
-        if (ok) mma_commit(&bars[WB_FEMPTY + fs]);
+        if (ok) { if (elect_one()) mma_commit_raw(&bars[WB_FEMPTY + fs]); __syncwarp(); }
       }
-      mma_commit(&bars[WB_DONE]);
+      if (elect_one()) mma_commit_raw(&bars[WB_DONE]);
+      __syncwarp();
     }
     __syncwarp();
   } else if (has_work) {

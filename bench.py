@@ -42,40 +42,55 @@ def parse():
     return ap.parse_args()
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): one persistent
+    `nvidia-smi -lms 50` loop started before the warm-up; rows are time-stamped and filtered to [t0, t1]."""
+    Q = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
+        self.lock = threading.Lock()
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(',')])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
 
-    def summary(self):
+    def _read(self):
+        for line in self.proc.stdout:
+            with self.lock:
+                self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0=None, t1=None):
+        with self.lock:
+            rows = list(self.rows)
+        inside = [r for (t, r) in rows if t0 is None or (t0 <= t <= t1 + 0.05)]
+        where = 'timed region'
+        if len(inside) < 2:                        # region shorter than the sampling period: use the loaded window
+            inside = [r for (t, r) in rows if t0 is None or t >= t0 - 2.0]
+            where = 'warm-up + timed region'
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for r in inside:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for n, v in zip(names, r[4:8]):
+                sm.append(float(r[2])); mx.append(float(r[3]))
+                for n, v in zip(names, r[5:9]):
                     if v.lower().startswith('active'):
                         reasons.add(n)
             except Exception:
                 pass
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': where}
 
 
 def cpu_reference_leg(cfg_name, n_frames, threads=None):
@@ -189,12 +204,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
     # ---- timed region 1: resident inputs (value) + live per-kernel event timing ----
-    sampler = ClockSampler(local); sampler.start()
     lib.bhnerf_profile_begin()
+    t_region0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -205,7 +221,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     cat_ms = (ctypes.c_double * 5)(); cat_sc = (ctypes.c_int64 * 5)(); cat_ln = (ctypes.c_int64 * 5)()
     lib.bhnerf_profile_end(cat_ms, cat_sc, cat_ln)
-    clocks = sampler.summary()
+    clocks = sampler.summary(t_region0, time.time())
 
     # ---- timed region 2: end to end through the reference-facing API with HOST buffers ----
     ts = optimization.TrainStep.image(c['t_frames'], c['target'].reshape((Bt, S) if kind == 'lc' else (Bt, S, P)),
@@ -231,7 +247,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
-    sampler.stop_flag.set()
+    sampler.stop()
 
     # max over ranks
     if world > 1:
@@ -254,28 +270,45 @@ def main():
             pass
         tensor_peak = peaks.get('bf16_tflops_sustained', 1400.0)
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md)'
-        # dominant kernel = the category with the most device time
+        # per-kernel rooflines; the reported one is the kernel with the most device time
         names = ['render_fwd', 'render_bwd', 'wgrad', 'heads', 'misc']
         ms_by = {n: cat_ms[i] for i, n in enumerate(names)}
-        flops_by = {'render_fwd': FLOP_FWD, 'render_bwd': 49280 * 2, 'wgrad': 54656 * 2}   # fwd | dgrad chain | wgrad
-        dom = max(flops_by, key=lambda n: ms_by[n])
-        launches_dom = max(int(cat_sc[names.index(dom)]), 1)
-        per_launch_s = ms_by[dom] * 1e-3 / launches_dom
-        eval_per_launch = eval_per_step * args.steps / launches_dom
-        achieved = eval_per_launch * flops_by[dom] / per_launch_s / 1e12 if per_launch_s > 0 else 0.0
-        # DRAM bytes per launch of the dominant kernel: per-sample figure of the committed ncu --set full capture
-        # (profiles/ncu_traffic.json) x the evaluated samples of one launch
-        traffic = None
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        tc_on = impl == engine.IMPL_TC
+        # algorithmic work per evaluated sample: FLOPs of the MLP stage; bytes that must cross HBM
+        spec = {'render_fwd': dict(bound='tensor', flop=FLOP_FWD, bytes=1092 if tc_on else 2136),
+                'render_bwd': dict(bound='hbm' if tc_on else 'tensor', flop=49280 * 2, bytes=2084 if tc_on else 4184),
+                'wgrad': dict(bound='hbm' if tc_on else 'tensor', flop=54656 * 2, bytes=2144 if tc_on else 4180)}
         try:
-            per_sample = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))[dom + '_' + impl_name]
-            traffic = per_sample['dram_bytes_per_eval_sample'] * eval_per_launch
+            ncu_traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
         except Exception:
-            pass
-        roofline = {'bound': 'tensor', 'kernel': dom + '_' + impl_name, 'achieved': achieved, 'peak': tensor_peak,
-                    'unit': 'TFLOP/s', 'frac': achieved / tensor_peak, 'traffic': traffic, 'peak_source': peak_src,
-                    'avg_launch_ms': per_launch_s * 1e3, 'algorithmic_flop_per_sample': flops_by[dom],
+            ncu_traffic = {}
+        kernels = {}
+        for n, sp in spec.items():
+            launches = max(int(cat_sc[names.index(n)]), 1)
+            per_launch_s = ms_by[n] * 1e-3 / launches
+            eval_per_launch = eval_per_step * args.steps / launches
+            if per_launch_s <= 0:
+                continue
+            tf = eval_per_launch * sp['flop'] / per_launch_s / 1e12
+            gbs = eval_per_launch * sp['bytes'] / per_launch_s / 1e9
+            tr = ncu_traffic.get(n + '_' + impl_name, {}).get('dram_bytes_per_eval_sample')
+            k = {'bound': sp['bound'], 'avg_launch_ms': per_launch_s * 1e3, 'algorithmic_tflops': tf, 'algorithmic_gbs': gbs,
+                 'ms_per_step': ms_by[n] / args.steps, 'traffic': tr * eval_per_launch if tr else None}
+            if sp['bound'] == 'tensor':
+                k.update(achieved=tf, peak=tensor_peak, unit='TFLOP/s', frac=tf / tensor_peak)
+            else:
+                k.update(achieved=gbs, peak=hbm_peak, unit='GB/s', frac=gbs / hbm_peak)
+            kernels[n + '_' + impl_name] = k
+        dom = max(kernels, key=lambda n: kernels[n]['ms_per_step'])
+        kd = kernels[dom]
+        roofline = {'bound': kd['bound'], 'kernel': dom, 'achieved': kd['achieved'], 'peak': kd['peak'], 'unit': kd['unit'],
+                    'frac': kd['frac'], 'traffic': kd['traffic'],
+                    'peak_source': peak_src + ('; hbm_gbs' if kd['bound'] == 'hbm' else ''),
+                    'avg_launch_ms': kd['avg_launch_ms'], 'kernels': kernels,
                     'kernel_ms_per_step': {n: ms_by[n] / args.steps for n in names},
-                    'step_algorithmic_tflops': eval_per_step * (FLOP_FWD + FLOP_BWD) * args.steps / (ms * 1e-3) / 1e12}
+                    'step_algorithmic_tflops': eval_per_step * (FLOP_FWD + FLOP_BWD) * args.steps / (ms * 1e-3) / 1e12,
+                    'step_frac_of_tensor_peak': eval_per_step * (FLOP_FWD + FLOP_BWD) * args.steps / (ms * 1e-3) / 1e12 / tensor_peak}
         cpu = None
         if not args.no_cpu_baseline:
             nfr = args.cpu_frames or 8

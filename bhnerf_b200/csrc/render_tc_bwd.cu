@@ -18,7 +18,8 @@ namespace {
 // =====================================================================================================
 // dgrad chain
 // =====================================================================================================
-constexpr int kDThreads = 320;
+constexpr int kDThreads = 576;           // 16 epilogue warps + MMA issuer + weight loader
+constexpr int kDMmaWarp = 16;
 constexpr uint32_t DW_BYTES = TC_W_BYTES - 16384u;                 // stages of layers 1..3, contiguous in ws
 constexpr uint32_t D_SM_W = 0;
 constexpr uint32_t D_SM_W4 = DW_BYTES;                             // 128 floats
@@ -57,19 +58,19 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
 
   if (tid == 0) {
     mbar_init(&bars[DB_WFULL], 1);
-    mbar_init(&bars[DB_AREADY + 0], 4); mbar_init(&bars[DB_AREADY + 1], 4);
+    mbar_init(&bars[DB_AREADY + 0], 8); mbar_init(&bars[DB_AREADY + 1], 8);
     mbar_init(&bars[DB_DREADY + 0], 1); mbar_init(&bars[DB_DREADY + 1], 1);
     *abort_s = 0;
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(tmem_base_s, 512);
+  if (warp == kDMmaWarp) tmem_alloc(tmem_base_s, 512);
   if (tid < 128) w4s[tid] = ((const float*)(ws + TC_WS_CONST))[TC_C_W4 + tid];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tbase = *tmem_base_s;
 
-  if (warp == 9) {
+  if (warp == kDMmaWarp + 1) {
     if (lane == 0) {      // resident weights: layers 1..3 [hi|lo] images, one shot
       mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
       const uint8_t* src = ws + TC_WS_WB + 16384u;
@@ -78,7 +79,7 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
       bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
     }
     __syncwarp();
-  } else if (warp == 8) {
+  } else if (warp == kDMmaWarp) {
     {   // whole warp runs the loop; elect.sync inside the issue wrappers picks the issuing lane
       const uint32_t idesc = make_idesc(128, 128, 0, 0);      // A from TMEM, B K-major
       uint32_t a_phase[2] = {0u, 0u};
@@ -116,8 +117,10 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
     }
     __syncwarp();
   } else {
-    const int slot = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    // epilogue warps: (slot, column half, TMEM lane quadrant); thread = one sample row x 64 columns
+    const int slot = warp >> 3, half = (warp >> 2) & 1, q = warp & 3, row = q * 32 + lane;
     const uint32_t t_lane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 256u;
+    const int cg0 = half * 8;                      // first 8-column group of this warp
     uint32_t d_phase = 0;
     float db4 = 0.f;
     bool ok = true;
@@ -132,6 +135,10 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
       const int i = tile * 128 + row;
       const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
       uint8_t* del_tile = deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+      // ReLU masks of this row's 64 columns: the saved bf16 activations, loaded ahead of their use
+      uint4 h[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) h[g] = *reinterpret_cast<const uint4*>(act_tile + 3 * lstride + sample_img_off(row, cg0 + g));
       // d loss / d o = e(1-e) * sum_c dI[b,c,ray] * w[c,i]   (sigmoid', network.py:230; kgeo.py:621)
       const int ray = v.ray[i];
       const float e = e_saved[(size_t)b * v.n_pad + i];
@@ -139,68 +146,73 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
       if (ray >= 0)
         for (int c = 0; c < v.S; ++c) g += d_images[((size_t)b * v.S + c) * v.P + ray] * v.w[(size_t)c * v.n_pad + i];
       const float dout = g * e * (1.f - e);
-      db4 += dout;
-      {   // aux image [128][16]: col 0 = bf16 hi part of dout, col 1 = lo part
+      if (half == 0) {
+        db4 += dout;
+        // aux image [128][16]: col 0 = bf16 hi part of dout, col 1 = lo part
         uint8_t* aux = deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
         const float dh = __bfloat162float(__float2bfloat16_rn(dout));
         *reinterpret_cast<uint4*>(aux + sample_img_off(row, 0)) = make_uint4(pack_bf16x2(dh, dout - dh), 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(aux + sample_img_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
       // delta_3[j] = dout * W4[j] * (h3[j] > 0)
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
         uint32_t d[16], dl[16];
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
-          const uint32_t off = sample_img_off(row, (c0 >> 3) + gq);
-          uint4 h = *reinterpret_cast<const uint4*>(act_tile + 3 * lstride + off);
-          const float* w4 = w4s + c0 + 8 * gq;
-          delta_pack<PL>(h.x, dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
-          delta_pack<PL>(h.y, dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
-          delta_pack<PL>(h.z, dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
-          delta_pack<PL>(h.w, dout * w4[6], dout * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
+          const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
+          const uint4 hh = h[4 * cc + gq];
+          const float* w4 = w4s + (cg0 + 4 * cc + gq) * 8;
+          delta_pack<PL>(hh.x, dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
+          delta_pack<PL>(hh.y, dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
+          delta_pack<PL>(hh.z, dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
+          delta_pack<PL>(hh.w, dout * w4[6], dout * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
           *reinterpret_cast<uint4*>(del_tile + 3 * lstride + off) =
               make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]);
           if (PL == 2)
             *reinterpret_cast<uint4*>(del_tile + pstride + 3 * lstride + off) =
                 make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
         }
-        tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), d);
-        if (PL == 2) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), dl);
+        tmem_st16(t_lane + 128u + (uint32_t)(half * 32 + cc * 16), d);
+        if (PL == 2) tmem_st16(t_lane + 192u + (uint32_t)(half * 32 + cc * 16), dl);
       }
       tmem_wait_st();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
       for (int l = 3; l >= 1; --l) {       // D = delta_l * W_l^T  ->  delta_{l-1}
+        const uint8_t* h_img = act_tile + (size_t)(l - 1) * lstride;
+        uint8_t* d_img = del_tile + (size_t)(l - 1) * lstride;
+#pragma unroll
+        for (int gI = 0; gI < 8; ++gI) h[gI] = *reinterpret_cast<const uint4*>(h_img + sample_img_off(row, cg0 + gI));
         ok = wait(&bars[DB_DREADY + slot], d_phase, ab);
         if (!ok) break;
         d_phase ^= 1u;
         tc_fence_after_sync();
-        const uint8_t* h_img = act_tile + (size_t)(l - 1) * lstride;
-        uint8_t* d_img = del_tile + (size_t)(l - 1) * lstride;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t raw[32], d[16], dl[16];
-          tmem_ld32(t_lane + (uint32_t)c0, raw);
-          tmem_wait_ld();
+        uint32_t raw[2][32];
+        tmem_ld32(t_lane + (uint32_t)(half * 64), raw[0]);
+        tmem_ld32(t_lane + (uint32_t)(half * 64 + 32), raw[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t d[16], dl[16];
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
-            const uint32_t off = sample_img_off(row, (c0 >> 3) + gq);
-            uint4 h = *reinterpret_cast<const uint4*>(h_img + off);
-            const uint32_t* rr = raw + 8 * gq;
-            delta_pack<PL>(h.x, __uint_as_float(rr[0]), __uint_as_float(rr[1]), d[4 * gq + 0], dl[4 * gq + 0]);
-            delta_pack<PL>(h.y, __uint_as_float(rr[2]), __uint_as_float(rr[3]), d[4 * gq + 1], dl[4 * gq + 1]);
-            delta_pack<PL>(h.z, __uint_as_float(rr[4]), __uint_as_float(rr[5]), d[4 * gq + 2], dl[4 * gq + 2]);
-            delta_pack<PL>(h.w, __uint_as_float(rr[6]), __uint_as_float(rr[7]), d[4 * gq + 3], dl[4 * gq + 3]);
+            const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
+            const uint4 hh = h[4 * cc + gq];
+            const uint32_t* rr = raw[cc] + 8 * gq;
+            delta_pack<PL>(hh.x, __uint_as_float(rr[0]), __uint_as_float(rr[1]), d[4 * gq + 0], dl[4 * gq + 0]);
+            delta_pack<PL>(hh.y, __uint_as_float(rr[2]), __uint_as_float(rr[3]), d[4 * gq + 1], dl[4 * gq + 1]);
+            delta_pack<PL>(hh.z, __uint_as_float(rr[4]), __uint_as_float(rr[5]), d[4 * gq + 2], dl[4 * gq + 2]);
+            delta_pack<PL>(hh.w, __uint_as_float(rr[6]), __uint_as_float(rr[7]), d[4 * gq + 3], dl[4 * gq + 3]);
             *reinterpret_cast<uint4*>(d_img + off) = make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]);
             if (PL == 2)
               *reinterpret_cast<uint4*>(d_img + pstride + off) =
                   make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
           }
           if (l > 1) {
-            tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), d);
-            if (PL == 2) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), dl);
+            tmem_st16(t_lane + 128u + (uint32_t)(half * 32 + cc * 16), d);
+            if (PL == 2) tmem_st16(t_lane + 192u + (uint32_t)(half * 32 + cc * 16), dl);
           }
         }
         if (l > 1) {
@@ -218,7 +230,7 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tbase, 512);
+  if (warp == kDMmaWarp) tmem_dealloc(tbase, 512);
   if (tid == 0 && *abort_s) atomicExch(status + 1, 1);
 }
 

@@ -184,6 +184,50 @@ __global__ void loss_vis_kernel(const float2* __restrict__ vis, const float* __r
   if (threadIdx.x == 0) atomicAdd(loss, scale * tot);
 }
 
+// 'cphase' (network.py:555-559): closure phase = angle(v1*v2*v3) over the baseline-triangle axis of vis [Bt,3,V];
+// chisq = sum (1 - cos(target - cphase)) / sigma^2.  d cphase / d v_k = (-im_k, re_k) / |v_k|^2.
+__global__ void loss_cphase_kernel(const float2* __restrict__ vis, const float* __restrict__ target,
+                                   const float* __restrict__ sg, float scale, int V, int n,
+                                   float* __restrict__ loss, float2* __restrict__ dvis) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = i / V, v = i - b * V;
+    const size_t base = (size_t)b * 3 * V + v;
+    const float2 v1 = vis[base], v2 = vis[base + V], v3 = vis[base + 2 * (size_t)V];
+    const float pr = v1.x * v2.x - v1.y * v2.y, pi = v1.x * v2.y + v1.y * v2.x;
+    const float br = pr * v3.x - pi * v3.y, bi = pr * v3.y + pi * v3.x;
+    const float phi = atan2f(bi, br);
+    const float s2 = sg[i] * sg[i];
+    float sn, cs;
+    sincosf(target[i] - phi, &sn, &cs);
+    acc += (1.f - cs) / s2;
+    const float gphi = -scale * sn / s2;                   // d loss / d cphase
+    const float2 vv[3] = {v1, v2, v3};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float m2 = vv[k].x * vv[k].x + vv[k].y * vv[k].y;
+      const float f = (m2 > 0.f) ? gphi / m2 : 0.f;
+      dvis[base + (size_t)k * V] = make_float2(-f * vv[k].y, f * vv[k].x);
+    }
+  }
+  float tot = block_reduce_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, scale * tot);
+}
+
+// dst += src (chunked steps of the host mirror accumulate per-chunk gradients / losses on the device)
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+extern "C" int bhnerf_add_inplace(float* dst, const float* src, int32_t n, void* stream) {
+  BH_REQUIRE(dst && src && n > 0, "add_inplace: bad argument");
+  BhProfScope ps(BH_CAT_MISC, 1, (cudaStream_t)stream);
+  add_inplace_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, int32_t V, int32_t P, float* vis,
                               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -197,13 +241,17 @@ extern "C" int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, i
 extern "C" int bhnerf_loss_vis(const float* vis, const float* target, const float* sigma, float loss_scale,
                                int32_t kind, int32_t Bt, int32_t V, float* loss, float* d_vis, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  BH_REQUIRE(kind == BHNERF_LOSS_VIS || kind == BHNERF_LOSS_AMP, "loss_vis: eht dtype (%d) not supported", kind);
+  BH_REQUIRE(kind == BHNERF_LOSS_VIS || kind == BHNERF_LOSS_AMP || kind == BHNERF_LOSS_CPHASE,
+             "loss_vis: eht dtype (%d) not supported", kind);
   BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   int n = Bt * V;
   int blocks = (n + 255) / 256; if (blocks > 592) blocks = 592;
   BhProfScope ps(BH_CAT_HEADS, 1, st);
-  loss_vis_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, kind, n, loss,
-                                          (float2*)d_vis);
+  if (kind == BHNERF_LOSS_CPHASE)
+    loss_cphase_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, V, n, loss, (float2*)d_vis);
+  else
+    loss_vis_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, kind, n, loss,
+                                            (float2*)d_vis);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -204,12 +204,28 @@ def vis_fwd(A, images):
     return vis
 
 
+def add_inplace(dst, src):
+    """dst += src on the device.  C ABI: bhnerf_add_inplace."""
+    lib = _lib.load()
+    assert dst.numel() == src.numel() and dst.dtype == torch.float32 and src.dtype == torch.float32
+    with torch.cuda.device(dst.device):
+        check(lib.bhnerf_add_inplace(_ptr(dst), _ptr(src), dst.numel(), _stream()))
+    return dst
+
+
 def loss_vis(vis, target, sigma, scale, kind):
+    """(loss[1], d_vis).  'vis'/'amp': vis [Bt,V]; 'cphase': vis [Bt,3V] (baseline-triangle axis folded into V),
+    target/sigma [Bt,V].  C ABI: bhnerf_loss_vis (bhnerf/network.py:546-559)."""
     lib = _lib.load(); dev = vis.device
     Bt, V = vis.shape
     k = LOSS_KINDS[kind] if isinstance(kind, str) else kind
+    if k == LOSS_KINDS['cphase']:
+        assert V % 3 == 0
+        V //= 3
     target = _c64(target, dev) if k == LOSS_KINDS['vis'] else _dev_f32(target, dev)
     sigma = _dev_f32(sigma, dev)
+    if sigma.numel() == 1:
+        sigma = sigma.reshape(1).expand(Bt * V).contiguous()
     assert target.numel() == Bt * V and sigma.numel() == Bt * V
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     dvis = torch.empty_like(vis)

@@ -234,14 +234,21 @@ def loss_fn_image(params, predictor_fn, target, sigma, offset, t_frames, coords,
 def _eht_prepare(scene, target, sigma, A, dtype, Bt):
     if dtype not in ('vis', 'amp', 'cphase'):
         raise AttributeError('eht dtype ({}) not supported'.format(dtype))
-    if dtype == 'cphase':
-        raise NotImplementedError("eht dtype 'cphase' (closure phases, network.py:555-559) is not built yet")
     if scene.S != 1:
         raise NotImplementedError('polarized visibilities (A with a pol axis) are not built yet')
     A = engine._c64(A, scene.device)
+    tshape = tuple(np.shape(target)) if not isinstance(target, torch.Tensor) else tuple(target.shape)
+    if dtype == 'cphase':
+        # A (nt, 3, ncphase, npix): one DFT matrix per baseline of each triangle (network.py:555-559)
+        if A.dim() != 4 or A.shape[0] != Bt or A.shape[1] != 3 or A.shape[3] != scene.P:
+            raise AttributeError('A should have shape (nt, 3, ncphase, npix) = ({}, 3, V, {}), got {}'.format(
+                Bt, scene.P, tuple(A.shape)))
+        if len(tshape) != 2:
+            raise AttributeError('visibilities (ndim=3) should have +1 dimensions as target (ndim={}) for dtype={}'.format(
+                len(tshape), dtype))
+        return A.reshape(Bt, 3 * A.shape[2], scene.P)      # triangle axis folded into the row axis
     if A.dim() != 3 or A.shape[0] != Bt or A.shape[2] != scene.P:
         raise AttributeError('A should have shape (nt, nvis, npix) = ({}, V, {}), got {}'.format(Bt, scene.P, tuple(A.shape)))
-    tshape = tuple(np.shape(target)) if not isinstance(target, torch.Tensor) else tuple(target.shape)
     if len(tshape) != 2:
         raise AttributeError('visibilities (ndim=2) should have same dimensions as target (ndim={}) for dtype={}'.format(len(tshape), dtype))
     return A
@@ -249,7 +256,7 @@ def _eht_prepare(scene, target, sigma, A, dtype, Bt):
 
 def loss_fn_eht(params, predictor_fn, target, sigma, A, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs,
                 t_geos, t_injection, scale, t_units, dtype, impl=None):
-    """bhnerf/network.py:486-564 ('vis' and 'amp')."""
+    """bhnerf/network.py:486-564 ('vis', 'amp', 'cphase')."""
     pred = _predictor_of(predictor_fn)
     scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units)
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
@@ -326,8 +333,8 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
         l, dvis = engine.loss_vis(vis, tgt[sl], sig[sl], float(scale), dtype)
         dI = engine.vis_bwd(A[sl].contiguous(), dvis, scene.P)
         g = engine.render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)
-        loss = l if loss is None else loss + l             # sums of per-chunk partials (host-side plumbing)
-        grads = g if grads is None else grads + g
+        loss = l if loss is None else engine.add_inplace(loss, l)       # per-chunk partials accumulate on the device
+        grads = g if grads is None else engine.add_inplace(grads, g)
         imgs.append(images)
     images = imgs[0] if len(imgs) == 1 else torch.cat(imgs, dim=0)
     state = _pmean_and_apply(state, grads)

@@ -39,14 +39,18 @@ def run_golden_case(case, impl=None, max_workspace=None):
     params = torch.as_tensor(d['params_flat'], device=dev)
     t_frames = torch.as_tensor(d['t_frames'].astype(np.float32), device=dev)
     A_, B_ = scene.image_shape
-    if case == 'case_vis':
+    if case in ('case_vis', 'case_amp', 'case_cphase'):
+        kind = case[5:]
         A = torch.as_tensor(d['A'], device=dev)
+        if kind == 'cphase':                                   # (nt,3,V,P): triangle axis folded into the row axis
+            A = A.reshape(A.shape[0], 3 * A.shape[2], A.shape[3])
         images, e, acts = engine.render_fwd(scene, params, t_frames, impl_i, save_acts=True)
         vis = engine.vis_fwd(A, images)
-        loss, dvis = engine.loss_vis(vis, d['target'], d['sigma'], 1.0, 'vis')
+        loss, dvis = engine.loss_vis(vis, d['target'], d['sigma'], 1.0, kind)
         dI = engine.vis_bwd(A, dvis, scene.P)
         grads = engine.render_bwd(scene, params, t_frames, dI, e, acts, impl_i)
-        extra = {'vis_err': rel_err(vis.cpu().numpy(), d['vis'])}
+        v = vis.cpu().numpy().reshape(d['vis'].shape)
+        extra = {'vis_err': float(np.abs(v - d['vis']).max() / np.abs(d['vis']).max())}
     else:
         kind = 'full' if case == 'case_image_full' else 'lc'
         tgt = d['target']

@@ -103,7 +103,9 @@ int bhnerf_loss_image(const float* images, const float* target, const float* sig
                       int32_t P, float* loss, float* d_images, void* stream);
 /* eht: loss_fn_eht (bhnerf/network.py:486-564).  A [Bt,V,P] complex64 (one DFT matrix per
  * frame), images [Bt,P] (S must be 1), target [Bt,V] complex64 ('vis') or fp32 ('amp'),
- * sigma [Bt,V].  vis [Bt,V] complex64 overwritten.                                           */
+ * sigma [Bt,V].  vis [Bt,V] complex64 overwritten.
+ * 'cphase' (network.py:555-559): A is [Bt,3,V,P] = call vis_fwd/vis_bwd with 3V rows; loss_vis then takes
+ * vis/d_vis [Bt,3,V], target (radians) and sigma [Bt,V], and V = number of closure phases.      */
 int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, int32_t V, int32_t P,
                    float* vis, void* stream);
 int bhnerf_loss_vis(const float* vis, const float* target, const float* sigma, float loss_scale,
@@ -141,6 +143,8 @@ int bhnerf_radiative_transfer(const float* emission, const float* g, const float
  * TrainState.apply_gradients (bhnerf/network.py:171-182, :621).  grad_scale multiplies the
  * gradient first (1/ndev turns an all-reduce SUM into jax.lax.pmean, network.py:620).
  * count = number of updates already applied.                                                 */
+/* dst[n] += src[n] on the device (per-chunk gradients / losses of the chunked eht step) */
+int bhnerf_add_inplace(float* dst, const float* src, int32_t n, void* stream);
 int bhnerf_adam_step(float* params, const float* grads, float* mu, float* nu, int32_t n,
                      int32_t count, float lr_init, float lr_final, int32_t transition_steps,
                      float b1, float b2, float eps, float grad_scale, void* stream);

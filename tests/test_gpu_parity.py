@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(__file__), 'golden')
 IMG_TOL, GRAD_TOL = 1e-4, 1e-3
-CASES = ['case_image_full', 'case_lc_QU', 'case_lc_IQU', 'case_vis']
+CASES = ['case_image_full', 'case_lc_QU', 'case_lc_IQU', 'case_vis', 'case_amp', 'case_cphase']
 
 
 def _impls():
@@ -166,6 +166,35 @@ def test_reference_api_train_step_matches_oracle(impl):
     tot, frames = optimization.total_movie_loss(2, pred.init_state(params), ts, rt, return_frames=True)
     assert abs(tot - float(d['loss']) / 4) / (float(d['loss']) / 4) < IMG_TOL
     assert frames.shape == (4, 16, 16)
+
+
+@pytest.mark.parametrize('dtype', ['vis', 'amp', 'cphase'])
+def test_reference_api_eht_step_matches_oracle(dtype):
+    """TrainStep.eht -> network.gradient_step_eht / test_eht (optimization.py:218-268, network.py:624-682, :741-795):
+    loss and the first Adam update against the oracle's value_and_grad for every eht dtype."""
+    from collections import OrderedDict
+    from bhnerf_b200 import network, optimization
+    from oracle import bhnerf_oracle as O
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    d = np.load(os.path.join(G, 'case_%s.npz' % dtype))
+    pred = network.NeRF_Predictor(float(d['scale']), float(d['rmin']), float(d['rmax']), float(d['z_width']))
+    params = network.unflatten_params(d['params_flat'])
+    state = pred.init_state(params, num_iters=100, lr_init=1e-3, lr_final=1e-5)
+    rt = OrderedDict(coords=geo['coords'], Omega=geo['Omega'], J=1.0, g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
+                     t_start_obs=float(d['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d['t_injection']))
+    ts = optimization.TrainStep.eht(d['t_frames'], d['target'], d['sigma'], d['A'], dtype=dtype)
+    loss0, _, images = ts(state, rt, np.arange(4), update_state=False)
+    assert abs(loss0.item() - float(d['loss'])) / abs(float(d['loss'])) < IMG_TOL
+    assert np.abs(images.cpu().numpy() - d['images'].reshape(images.shape)).max() / np.abs(d['images']).max() < IMG_TOL
+    loss, state, images = ts(state, rt, np.arange(4))
+    assert abs(loss.item() - float(d['loss'])) / abs(float(d['loss'])) < IMG_TOL
+    want, _, _ = O.adam_step(d['params_flat'].astype(np.float64), d['grads'], np.zeros(55169), np.zeros(55169), 0,
+                             1e-3, 1e-5, 100)
+    got = state.flat.cpu().numpy()
+    upd_err = np.abs((got - d['params_flat']) - (want - d['params_flat'])).max() / 1e-3
+    assert upd_err < 2e-2, upd_err
+    with pytest.raises(AttributeError):
+        optimization.TrainStep.eht(d['t_frames'], d['target'], d['sigma'], d['A'], dtype='bogus')(state, rt, np.arange(4))
 
 
 def test_predictor_apply_and_sample_3d_grid_vs_oracle():

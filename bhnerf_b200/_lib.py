@@ -35,6 +35,7 @@ SIGNATURES = {
     'bhnerf_fwd_workspace_bytes': (_sz, [_i32]),
     'bhnerf_render_fwd': (C.c_int, [_SP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     'bhnerf_bwd_workspace_bytes': (_sz, [_SP, _i32, _i32]),
+    'bhnerf_bwd_fixed_workspace_bytes': (_sz, [_SP, _i32, _i32]),
     'bhnerf_render_bwd': (C.c_int, [_SP, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     'bhnerf_loss_image': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     'bhnerf_vis_fwd': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),

@@ -105,9 +105,15 @@ extern "C" size_t bhnerf_acts_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_
   return acts_bytes_per_frame(sc, impl, bh_tc_planes(sc->n_active, Bt)) * (size_t)Bt;
 }
 
-// fixed (frame-count independent) part of the backward workspace
-static size_t bwd_fixed_bytes(int impl) {
-  return impl == BHNERF_IMPL_SIMT ? align_up(BH_SIMT_WT_FLOATS * 4, 256) : align_up(bh_tc_ws_bytes(), 256);
+// fixed (frame-count independent) part of the backward workspace: weight images (+ the delta ring of the fused
+// tcgen05 backward, one-plane plan)
+static size_t bwd_fixed_bytes(int impl, int pl) {
+  return impl == BHNERF_IMPL_SIMT ? align_up(BH_SIMT_WT_FLOATS * 4, 256)
+                                  : align_up(bh_tc_ws_bytes(), 256) + align_up(bh_tc_delta_fixed_bytes(pl), 256);
+}
+// where the backward's delta scratch lives: the fixed ring if the plan has one, else `per_chunk`
+static void* delta_ptr(char* ws, int impl, int pl, void* per_chunk) {
+  return (impl == BHNERF_IMPL_TC && bh_tc_delta_fixed_bytes(pl) > 0) ? (void*)(ws + align_up(bh_tc_ws_bytes(), 256)) : per_chunk;
 }
 // per-frame scratch of the backward beyond saved activations
 static size_t bwd_frame_bytes(const bhnerf_scene_t* sc, int impl, int pl) {
@@ -140,8 +146,12 @@ extern "C" int bhnerf_render_fwd(const bhnerf_scene_t* sc, const float* params, 
 extern "C" size_t bhnerf_bwd_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
   // enough for ONE frame of recompute; more lets the backward chunk more frames per launch
   const int pl = bh_tc_planes(sc->n_active, Bt);
-  return bwd_fixed_bytes(impl) + acts_bytes_per_frame(sc, impl, pl) + bwd_frame_bytes(sc, impl, pl) +
+  return bwd_fixed_bytes(impl, pl) + acts_bytes_per_frame(sc, impl, pl) + bwd_frame_bytes(sc, impl, pl) +
          (size_t)sc->n_pad * 4 + 1024;
+}
+// the frame-count independent part of bhnerf_bwd_workspace_bytes / bhnerf_train_workspace_bytes
+extern "C" size_t bhnerf_bwd_fixed_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
+  return bwd_fixed_bytes(impl, bh_tc_planes(sc->n_active, Bt));
 }
 
 extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, const float* t_frames, int32_t Bt,
@@ -154,11 +164,11 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
   PackedView v = bh_view(sc);
   FrameConsts fc = frame_consts(sc);
   char* ws = (char*)workspace;
-  size_t fixed = bwd_fixed_bytes(impl);
+  const int pl = bh_tc_planes(sc->n_active, Bt);
+  size_t fixed = bwd_fixed_bytes(impl, pl);
   BH_REQUIRE(workspace_bytes >= fixed, "render_bwd: workspace too small");
   char* p = ws + fixed;
   size_t avail = workspace_bytes - fixed;
-  const int pl = bh_tc_planes(sc->n_active, Bt);
   size_t per_frame = bwd_frame_bytes(sc, impl, pl) + (acts_saved ? 0 : acts_bytes_per_frame(sc, impl, pl)) +
                      (e_saved && acts_saved ? 0 : (size_t)sc->n_pad * 4);
   int Bc = per_frame ? (int)(avail / per_frame) : Bt;
@@ -171,7 +181,7 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
   for (int b0 = 0; b0 < Bt; b0 += Bc) {
     int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
     char* q = p;
-    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl, pl) * nb;
+    float* delta = (float*)delta_ptr(ws, impl, pl, q); q += bwd_frame_bytes(sc, impl, pl) * nb;
     const void* acts = acts_saved ? (const char*)acts_saved + acts_bytes_per_frame(sc, impl, pl) * b0 : nullptr;
     const float* e = e_saved ? e_saved + (size_t)b0 * sc->n_pad : nullptr;
     if (recompute) {
@@ -201,7 +211,8 @@ static size_t train_frame_bytes(const bhnerf_scene_t* sc, int impl, int pl) {
 }
 extern "C" size_t bhnerf_train_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
   // all Bt frames in one chunk; smaller workspaces are accepted down to one frame
-  return bwd_fixed_bytes(impl) + train_frame_bytes(sc, impl, bh_tc_planes(sc->n_active, Bt)) * (size_t)Bt + 1024;
+  const int pl = bh_tc_planes(sc->n_active, Bt);
+  return bwd_fixed_bytes(impl, pl) + train_frame_bytes(sc, impl, pl) * (size_t)Bt + 1024;
 }
 
 int bh_loss_image_accum(const float* images, const float* target, const float* sigma, const float* offset,
@@ -220,8 +231,8 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
   PackedView v = bh_view(sc);
   FrameConsts fc = frame_consts(sc);
   char* ws = (char*)workspace;
-  size_t fixed = bwd_fixed_bytes(impl);
   const int pl = bh_tc_planes(sc->n_active, Bt);
+  size_t fixed = bwd_fixed_bytes(impl, pl);
   size_t per_frame = train_frame_bytes(sc, impl, pl);
   BH_REQUIRE(workspace_bytes >= fixed + per_frame, "train_step_image: workspace (%zu B) cannot hold one frame (%zu B)",
              workspace_bytes, fixed + per_frame);
@@ -235,7 +246,7 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
     int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
     char* q = ws + fixed;
     void* acts = q; q += acts_bytes_per_frame(sc, impl, pl) * nb;
-    float* delta = (float*)q; q += bwd_frame_bytes(sc, impl, pl) * nb;
+    float* delta = (float*)delta_ptr(ws, impl, pl, q); q += bwd_frame_bytes(sc, impl, pl) * nb;
     float* e = (float*)q; q += (size_t)sc->n_pad * 4 * nb;
     float* dI = (float*)q;
     float* img = images + (size_t)b0 * sc->S * sc->P;

@@ -9,6 +9,15 @@
 //   tc_wgrad_kernel : dW_l^T[n][k] = sum_s delta_l[s][n] * in_l[s][k] as MN-major x MN-major UMMAs over the sample
 //                     axis, accumulated in TMEM (496 of 512 columns) across all tiles of a persistent CTA; bias
 //                     gradients ride on the constant-one column of the feature image, dW4 on the aux image.
+//   tc_bwd_fused_kernel : both roles in ONE launch as a cluster of two CTAs (rank 0 = dgrad, rank 1 = wgrad) per SM
+//                     pair.  The delta images go from the dgrad CTA to its partner through a small per-pair ring in
+//                     global memory that stays L2-resident (74 pairs x 4 tile sets x 132 KB = 39 MB) instead of a
+//                     per-frame HBM buffer; the hand-shake is mbarriers in the PARTNER's shared memory (remote arrive,
+//                     acquire/release at cluster scope).  DSMEM itself is not the data path: measured 21 B/clk per
+//                     SM (scripts/run_dsmem_probe.py), half of what the pair needs.  The single-SM fusion does not
+//                     fit: the wgrad accumulators take 464 of 512 TMEM columns and the two-plane weights 208 of
+//                     227 KB of shared memory.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -25,7 +34,14 @@ constexpr uint32_t D_SM_W = 0;
 constexpr uint32_t D_SM_W4 = DW_BYTES;                             // 128 floats
 constexpr uint32_t D_SM_BARS = D_SM_W4 + 512;
 constexpr uint32_t D_SM_TOTAL = D_SM_BARS + 128;
-enum { DB_WFULL = 0, DB_AREADY = 1, DB_DREADY = 3 };
+constexpr int kRingDepth = 4;                                      // tile sets per CTA pair in the global delta ring
+constexpr uint32_t TSET_BYTES = 4u * TC_SIMG_BYTES + TC_AIMG_BYTES; // delta_0..3 images + aux image of one tile
+enum { DB_WFULL = 0, DB_AREADY = 1, DB_DREADY = 3, DB_GFREE = 5 /* x kRingDepth, arrived by the wgrad CTA */ };
+// fused mode: where the partner CTA of the pair is
+struct PairLink {
+  uint8_t* ring;          // this pair's kRingDepth tile sets in global memory
+  uint32_t peer_bars;     // shared::cluster address of the partner's link barriers (wgrad: GFULL[d][l]; dgrad: GFREE[d])
+};
 
 __device__ __forceinline__ uint32_t relu_mask2(uint32_t h2, uint32_t d2) {   // keep the bf16 halves of d2 where h2 > 0
   uint32_t m = ((h2 & 0x00007fffu) ? 0x0000ffffu : 0u) | ((h2 & 0x7fff0000u) ? 0xffff0000u : 0u);
@@ -40,16 +56,16 @@ __device__ __forceinline__ void delta_pack(uint32_t h2, float a, float b, uint32
   if (PL == 2) lo = relu_mask2(h2, pack_bf16x2(a - bf16_lo(p), b - bf16_hi(p)));
 }
 
-template <int PL>
-__global__ void __launch_bounds__(kDThreads, 1)
-tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
-                const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
-                float* __restrict__ d_params, int* __restrict__ status) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+template <int PL, bool FUSED>
+__device__ __forceinline__ void
+dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, const PackedView& v,
+           const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
+           const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
+           float* __restrict__ d_params, int* __restrict__ status) {
   uint8_t* wsm = smem + D_SM_W;
   float* w4s = (float*)(smem + D_SM_W4);
   uint64_t* bars = (uint64_t*)(smem + D_SM_BARS);
-  uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
+  uint32_t* tmem_base_s = (uint32_t*)(bars + 10);
   int* abort_s = (int*)(tmem_base_s + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_per_frame = v.n_pad / 128;
@@ -60,6 +76,7 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
     mbar_init(&bars[DB_WFULL], 1);
     mbar_init(&bars[DB_AREADY + 0], 8); mbar_init(&bars[DB_AREADY + 1], 8);
     mbar_init(&bars[DB_DREADY + 0], 1); mbar_init(&bars[DB_DREADY + 1], 1);
+    for (int d = 0; d < kRingDepth; ++d) mbar_init(&bars[DB_GFREE + d], 1);
     *abort_s = 0;
     mbar_fence_init();
   }
@@ -67,6 +84,7 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
   if (tid < 128) w4s[tid] = ((const float*)(ws + TC_WS_CONST))[TC_C_W4 + tid];
   tc_fence_before_sync();
   __syncthreads();
+  if (FUSED) cluster_sync_all();          // the partner's barriers exist before anyone arrives on them
   tc_fence_after_sync();
   const uint32_t tbase = *tmem_base_s;
 
@@ -85,7 +103,7 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
       uint32_t a_phase[2] = {0u, 0u};
       bool ok = wait(&bars[DB_WFULL], 0, ab);
       for (int r = 0; ok; ++r) {
-        int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
+        int T0 = (r * ncta + cta) * 2;
         if (T0 >= NT) break;
         for (int l = 3; l >= 1 && ok; --l) {
           const uint32_t wl = smem_u32(wsm) + tc_stage_off(l) - 16384u;
@@ -127,14 +145,27 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
     const size_t act_fs = tc_acts_bytes_per_frame(v.n_pad, PL), del_fs = tc_delta_bytes_per_frame(v.n_pad, PL);
     const size_t lstride = (size_t)v.n_pad * 256u, pstride = (size_t)v.n_pad * 1024u;
     for (int r = 0; ok; ++r) {
-      int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
+      int T0 = (r * ncta + cta) * 2;
       if (T0 >= NT) break;
       int T = T0 + slot;
       if (T >= NT) continue;
       const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
       const int i = tile * 128 + row;
       const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
-      uint8_t* del_tile = deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+      // delta images of this tile: the per-frame scratch, or (fused) tile set `rd` of the pair's ring
+      const uint32_t rk = (uint32_t)(2 * r + slot), rd = rk % kRingDepth;
+      uint8_t* del_tile = FUSED ? link.ring + (size_t)rd * TSET_BYTES : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+      const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
+      uint8_t* aux = FUSED ? del_tile + 4u * TC_SIMG_BYTES
+                           : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
+      // tell the wgrad CTA that delta_l (and, with l = 3, the aux image) of this tile is in the ring
+      auto publish = [&](int l) {
+        if (FUSED) {
+          fence_proxy_async_global();       // generic-proxy stores -> the partner's cp.async.bulk reads (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(link.peer_bars + (rd * 4u + (uint32_t)l) * 8u);
+        }
+      };
       // ReLU masks of this row's 64 columns: the saved bf16 activations, loaded ahead of their use
       uint4 h[8];
 #pragma unroll
@@ -146,10 +177,13 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
       if (ray >= 0)
         for (int c = 0; c < v.S; ++c) g += d_images[((size_t)b * v.S + c) * v.P + ray] * v.w[(size_t)c * v.n_pad + i];
       const float dout = g * e * (1.f - e);
+      if (FUSED) {       // ring slot free: the partner has pulled tile rk - kRingDepth out of it
+        ok = wait_cluster(&bars[DB_GFREE + rd], ((rk / kRingDepth) & 1u) ^ 1u, ab);
+        if (!ok) break;
+      }
       if (half == 0) {
         db4 += dout;
         // aux image [128][16]: col 0 = bf16 hi part of dout, col 1 = lo part
-        uint8_t* aux = deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
         const float dh = __bfloat162float(__float2bfloat16_rn(dout));
         *reinterpret_cast<uint4*>(aux + sample_img_off(row, 0)) = make_uint4(pack_bf16x2(dh, dout - dh), 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(aux + sample_img_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
@@ -167,10 +201,10 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
           delta_pack<PL>(hh.y, dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
           delta_pack<PL>(hh.z, dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
           delta_pack<PL>(hh.w, dout * w4[6], dout * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
-          *reinterpret_cast<uint4*>(del_tile + 3 * lstride + off) =
+          *reinterpret_cast<uint4*>(del_tile + 3 * dls + off) =
               make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]);
           if (PL == 2)
-            *reinterpret_cast<uint4*>(del_tile + pstride + 3 * lstride + off) =
+            *reinterpret_cast<uint4*>(del_tile + pstride + 3 * dls + off) =
                 make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
         }
         tmem_st16(t_lane + 128u + (uint32_t)(half * 32 + cc * 16), d);
@@ -180,9 +214,10 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
+      publish(3);
       for (int l = 3; l >= 1; --l) {       // D = delta_l * W_l^T  ->  delta_{l-1}
         const uint8_t* h_img = act_tile + (size_t)(l - 1) * lstride;
-        uint8_t* d_img = del_tile + (size_t)(l - 1) * lstride;
+        uint8_t* d_img = del_tile + (size_t)(l - 1) * dls;
 #pragma unroll
         for (int gI = 0; gI < 8; ++gI) h[gI] = *reinterpret_cast<const uint4*>(h_img + sample_img_off(row, cg0 + gI));
         ok = wait(&bars[DB_DREADY + slot], d_phase, ab);
@@ -221,6 +256,7 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
         }
+        publish(l - 1);
       }
     }
     // d b4 = sum dout (network.py:64 bias of the last Dense)
@@ -230,8 +266,19 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (FUSED) cluster_sync_all();          // no CTA of the pair leaves while the other may still arrive on its barriers
   if (warp == kDMmaWarp) tmem_dealloc(tbase, 512);
   if (tid == 0 && *abort_s) atomicExch(status + 1, 1);
+}
+
+template <int PL>
+__global__ void __launch_bounds__(kDThreads, 1)
+tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
+                const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
+                float* __restrict__ d_params, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  dgrad_role<PL, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, d_images, Bt, e_saved, acts,
+                        deltas, d_params, status);
 }
 
 // =====================================================================================================
@@ -246,7 +293,10 @@ template <int PL> struct WCfg {
   static constexpr uint32_t SM_BARS = SM_FEAT + 2 * W_FBUF;
   static constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 };
-enum { WB_FULL = 0, WB_EMPTY = 3, WB_FFULL = 6, WB_FEMPTY = 8, WB_DONE = 10 };
+// WB_GFULL[d][l]: delta_l (l = 3 also: aux) of the tile in ring set d is written; 8 remote arrivals (the dgrad
+// CTA's epilogue warps of that slot) per phase
+enum { WB_FULL = 0, WB_EMPTY = 3, WB_FFULL = 6, WB_FEMPTY = 8, WB_DONE = 10, WB_GFULL = 11, WB_NBARS = 11 + 4 * kRingDepth };
+static_assert(WB_NBARS * 8 + 16 <= 256, "wgrad barrier area");
 // TMEM accumulator columns (lane = n, or j for dW4)
 constexpr uint32_t ACC_W3 = 0, ACC_W3F = 128, ACC_W2 = 160, ACC_W1 = 288, ACC_W0F = 416, ACC_B2 = 448, ACC_B1 = 464,
                    ACC_W4 = 480;
@@ -262,15 +312,28 @@ template <int PL> __device__ __forceinline__ void wg_subjob(int idx, int& j, int
   else { j = 4; pa = idx - 12; pb = 0; }
 }
 
-template <int PL>
-__global__ void __launch_bounds__(kWThreads, 1)
-tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas,
-                float* __restrict__ d_params, int* __restrict__ status) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+// Tile order of one wgrad CTA.  Stand-alone: T = cta, cta + ncta, ...   Fused: the tile PAIRS of its dgrad partner,
+// (r * ncta + cta) * 2 + s for s = 0, 1 -- ring sequence number rk = 2r + s, the same numbering the dgrad CTA uses.
+// Returns 0 = done, 1 = tile T valid, 2 = skip (odd tail of the last pair).
+template <bool FUSED>
+__device__ __forceinline__ int wg_tile(int it, int cta, int ncta, int NT, int& T) {
+  if (!FUSED) { T = cta + it * ncta; return T < NT ? 1 : 0; }
+  const int T0 = ((it >> 1) * ncta + cta) * 2;
+  if (T0 >= NT) return 0;
+  T = T0 + (it & 1);
+  return T < NT ? 1 : 2;
+}
+
+template <int PL, bool FUSED>
+__device__ __forceinline__ void
+wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, int n_pad, int Bt,
+           const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas, float* __restrict__ d_params,
+           int* __restrict__ status) {
+  static_assert(!(FUSED && PL == 2), "the fused pair runs the one-plane plan");
   constexpr int kWStages = WCfg<PL>::kWStages;
   constexpr uint32_t W_SM_FEAT = WCfg<PL>::SM_FEAT, W_SM_BARS = WCfg<PL>::SM_BARS, W_FBUF = WCfg<PL>::W_FBUF;
   uint64_t* bars = (uint64_t*)(smem + W_SM_BARS);
-  uint32_t* tmem_base_s = (uint32_t*)(bars + 12);
+  uint32_t* tmem_base_s = (uint32_t*)(bars + WB_NBARS);
   int* abort_s = (int*)(tmem_base_s + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_per_frame = n_pad / 128;
@@ -283,25 +346,38 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
     for (int s = 0; s < kWStages; ++s) { mbar_init(&bars[WB_FULL + s], 1); mbar_init(&bars[WB_EMPTY + s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bars[WB_FFULL + s], 1); mbar_init(&bars[WB_FEMPTY + s], 1); }
     mbar_init(&bars[WB_DONE], 1);
+    for (int s = 0; s < 4 * kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], 8);
     *abort_s = 0;
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(tmem_base_s, 512);
   tc_fence_before_sync();
   __syncthreads();
+  if (FUSED) cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tbase = *tmem_base_s;
-  const bool has_work = (int)blockIdx.x < NT;
+  int T_first;
+  const bool has_work = wg_tile<FUSED>(0, cta, ncta, NT, T_first) == 1;
 
   if (warp == 5) {
     // ===================== producer: bulk copies of the saved images =====================
     if (lane == 0) {
       uint32_t cnt = 0, fcnt = 0;
       bool ok = true;
-      for (int T = blockIdx.x; T < NT && ok; T += gridDim.x, ++fcnt) {
+      for (int it = 0; ok; ++it) {
+        int T;
+        const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
+        if (tv == 0) break;
+        if (tv == 2) continue;
         const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
         const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
-        const uint8_t* del_tile = deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+        // fused: ring set rd; use number ru of that set selects the barrier phase
+        const uint32_t rd = (uint32_t)it % kRingDepth, ru = ((uint32_t)it / kRingDepth) & 1u;
+        const uint8_t* del_tile = FUSED ? link.ring + (size_t)rd * TSET_BYTES
+                                        : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+        const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;
+        const uint8_t* aux_src = FUSED ? del_tile + 4u * TC_SIMG_BYTES
+                                       : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
         {   // feature (+ lo plane) and aux images of this tile
           uint32_t fs = fcnt & 1u;
           ok = wait(&bars[WB_FEMPTY + fs], ((fcnt >> 1) & 1u) ^ 1u, ab);
@@ -311,8 +387,13 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
           mbar_expect_tx(&bars[WB_FFULL + fs], PL * TC_FIMG_BYTES + TC_AIMG_BYTES);
           bulk_g2s(dst, fsrc, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
           if (PL == 2) bulk_g2s(dst + TC_FIMG_BYTES, fsrc + (size_t)n_pad * 64u, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
-          bulk_g2s(dst + PL * TC_FIMG_BYTES, deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES,
-                   TC_AIMG_BYTES, &bars[WB_FFULL + fs]);
+          if (FUSED) {      // aux is published together with delta_3
+            ok = wait_cluster(&bars[WB_GFULL + rd * 4u + 3u], ru, ab);
+            if (!ok) break;
+            fence_proxy_async_global();
+          }
+          bulk_g2s(dst + PL * TC_FIMG_BYTES, aux_src, TC_AIMG_BYTES, &bars[WB_FFULL + fs]);
+          ++fcnt;
         }
         for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
           int j, pa, pb;
@@ -320,8 +401,13 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
           uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
           ok = wait(&bars[WB_EMPTY + st], ph ^ 1u, ab);
           if (!ok) break;
+          if (FUSED && j < 4) {       // delta_{3-j} of this tile has left the dgrad CTA
+            ok = wait_cluster(&bars[WB_GFULL + rd * 4u + (uint32_t)(3 - j)], ru, ab);
+            if (!ok) break;
+            fence_proxy_async_global();
+          }
           uint8_t* dst = smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES;
-          const uint8_t* a_src = (j < 4) ? del_tile + pa * pstride + (size_t)(3 - j) * lstride
+          const uint8_t* a_src = (j < 4) ? del_tile + pa * pstride + (size_t)(3 - j) * dls
                                          : act_tile + pa * pstride + 3 * lstride;
           mbar_expect_tx(&bars[WB_FULL + st], (j < 3) ? 2 * TC_SIMG_BYTES : TC_SIMG_BYTES);
           bulk_g2s(dst, a_src, TC_SIMG_BYTES, &bars[WB_FULL + st]);
@@ -340,7 +426,11 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
       bool ok = true;
       uint32_t later_tile = 0;               // 0 for the CTA's first tile: accumulators start from zero
       // all operands are [s][c] images read MN-major: K (= sample) groups advance by RS, M/N groups by CS
-      for (int T = blockIdx.x; T < NT && ok; T += gridDim.x, ++fcnt, later_tile = 1) {
+      for (int it = 0; ok; ++it) {
+        int T;
+        const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
+        if (tv == 0) break;
+        if (tv == 2) continue;
         uint32_t fs = fcnt & 1u;
         ok = wait(&bars[WB_FFULL + fs], (fcnt >> 1) & 1u, ab);
         if (!ok) break;
@@ -353,6 +443,11 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
           ok = wait(&bars[WB_FULL + st], ph, ab);
           if (!ok) break;
           tc_fence_after_sync();
+          // fused: delta_0 is the last image pulled out of the ring set -> hand the set back to the dgrad CTA
+          if (FUSED && j == 3) {
+            if (elect_one()) mbar_arrive_remote(link.peer_bars + ((uint32_t)it % kRingDepth) * 8u);
+            __syncwarp();
+          }
           const uint32_t A = smem_u32(smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES), B = A + TC_SIMG_BYTES;
           const uint32_t feat = fbuf + (uint32_t)pb * TC_FIMG_BYTES;
           const uint32_t started = later_tile | ((pa | pb) ? 1u : 0u);     // (hi,hi) is each accumulator's first product
@@ -385,12 +480,13 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
           __syncwarp();
         }
         if (ok) { if (elect_one()) mma_commit_raw(&bars[WB_FEMPTY + fs]); __syncwarp(); }
+        ++fcnt; later_tile = 1;
       }
       if (elect_one()) mma_commit_raw(&bars[WB_DONE]);
       __syncwarp();
     }
     __syncwarp();
-  } else if (has_work) {
+  } else if (warp < 4 && has_work) {
     // ===================== final epilogue: TMEM accumulators -> d_params (atomic accumulate) =====================
     bool ok = wait(&bars[WB_DONE], 0, ab);
     tc_fence_after_sync();
@@ -422,8 +518,40 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (FUSED) cluster_sync_all();
   if (warp == 4) tmem_dealloc(tbase, 512);
   if (tid == 0 && *abort_s) atomicExch(status + 2, 1);
+}
+
+template <int PL>
+__global__ void __launch_bounds__(kWThreads, 1)
+tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas,
+                float* __restrict__ d_params, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  wgrad_role<PL, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, n_pad, Bt, acts, deltas, d_params, status);
+}
+
+// =====================================================================================================
+// fused backward: cluster of two CTAs per SM pair, rank 0 = dgrad chain, rank 1 = wgrad (one-plane plan)
+// =====================================================================================================
+constexpr uint32_t F_SM_TOTAL = D_SM_TOTAL > WCfg<1>::SM_TOTAL ? D_SM_TOTAL : WCfg<1>::SM_TOTAL;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
+tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
+                    const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
+                    float* __restrict__ d_params, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  PairLink link;
+  link.ring = ring + (size_t)pair * kRingDepth * TSET_BYTES;
+  if (rank == 0) {
+    link.peer_bars = mapa_u32(smem_u32(smem + WCfg<1>::SM_BARS + WB_GFULL * 8), 1u);
+    dgrad_role<1, true>(smem, pair, npairs, link, v, ws, d_images, Bt, e_saved, acts, nullptr, d_params, status);
+  } else {
+    link.peer_bars = mapa_u32(smem_u32(smem + D_SM_BARS + DB_GFREE * 8), 0u);
+    wgrad_role<1, true>(smem, pair, npairs, link, v.n_pad, Bt, acts, nullptr, d_params, status);
+  }
 }
 
 int g_num_sms_b = 0;
@@ -436,11 +564,26 @@ int num_sms_b() {
   return g_num_sms_b;
 }
 
+bool bwd_fused_enabled() {                 // BHNERF_TC_FUSED=0 selects the two-kernel backward (A/B measurements)
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("BHNERF_TC_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
 template <int PL>
 int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int Bt, const float* e_saved, const void* acts,
                void* delta_ws, float* d_params, cudaStream_t st) {
   int* status = (int*)((uint8_t*)ws + TC_WS_STATUS);
   const int NT = Bt * (v.n_pad / 128);
+  if (PL == 1 && bwd_fused_enabled()) {
+    BhProfScope ps(BH_CAT_BWD, 1, st);
+    BH_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SM_TOTAL));
+    int npairs = (NT + 1) / 2; if (npairs > num_sms_b() / 2) npairs = num_sms_b() / 2;
+    tc_bwd_fused_kernel<<<2 * npairs, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, d_images, Bt, e_saved,
+                                                                 (const uint8_t*)acts, (uint8_t*)delta_ws, d_params, status);
+    BH_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   {
     BhProfScope ps(BH_CAT_BWD, 1, st);
     BH_CHECK_CUDA(cudaFuncSetAttribute(tc_dgrad_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SM_TOTAL));
@@ -462,7 +605,14 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
 
 }  // namespace
 
-size_t bh_tc_delta_bytes_per_frame(int n_pad, int planes) { return tc_delta_bytes_per_frame(n_pad, planes); }
+// Backward scratch beyond the saved activations.  One-plane plan: the fixed delta ring of the fused CTA pairs
+// (frame-count independent, L2-resident); two-plane plan or BHNERF_TC_FUSED=0: per-frame delta images.
+size_t bh_tc_delta_bytes_per_frame(int n_pad, int planes) {
+  return (planes == 1 && bwd_fused_enabled()) ? 0 : tc_delta_bytes_per_frame(n_pad, planes);
+}
+size_t bh_tc_delta_fixed_bytes(int planes) {
+  return (planes == 1 && bwd_fused_enabled()) ? (size_t)(num_sms_b() / 2) * kRingDepth * TSET_BYTES : 0;
+}
 
 int bh_tc_bwd(const PackedView& v, const void* ws, const float* params, const float* d_images, int Bt,
               const float* e_saved, const void* acts, void* delta_ws, int planes, float* d_params, cudaStream_t st) {

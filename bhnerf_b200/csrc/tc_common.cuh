@@ -61,6 +61,15 @@ __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, const Abort
   return false;
 }
 
+__device__ __forceinline__ bool wait_cluster(uint64_t* bar, uint32_t parity, const Abort& ab) {   // acquire.cluster
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    if ((i & 255u) == 255u && *ab.flag) return false;
+  }
+  *ab.flag = 1;
+  return false;
+}
+
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)),

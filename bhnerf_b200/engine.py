@@ -160,7 +160,8 @@ def render_bwd(scene, params, t_frames, d_images, e=None, acts=None, impl=None, 
     Bt = t_frames.numel()
     assert d_images.numel() == Bt * scene.S * scene.P
     one = lib.bhnerf_bwd_workspace_bytes(scene.ref, Bt, impl)
-    full = one + (one - 1024) * (Bt - 1)
+    fixed = lib.bhnerf_bwd_fixed_workspace_bytes(scene.ref, Bt, impl)
+    full = one + (one - fixed - 1024) * (Bt - 1)
     max_workspace = DEFAULT_MAX_WORKSPACE if max_workspace is None else max_workspace
     nbytes = max(one, min(full, int(max_workspace)))
     ws = workspace(nbytes, dev)

@@ -90,6 +90,9 @@ int bhnerf_render_fwd(const bhnerf_scene_t* scene, const float* params, const fl
  * the backward then recomputes them frame-chunk by frame-chunk inside `workspace`
  * (>= bhnerf_bwd_workspace_bytes).                                                           */
 size_t bhnerf_bwd_workspace_bytes(const bhnerf_scene_t* scene, int32_t Bt, int32_t impl);
+/* the frame-count independent part of the two workspace sizes above/below (weight images + the
+ * L2-resident delta ring of the fused tcgen05 backward); the rest scales with the frames per chunk */
+size_t bhnerf_bwd_fixed_workspace_bytes(const bhnerf_scene_t* scene, int32_t Bt, int32_t impl);
 int bhnerf_render_bwd(const bhnerf_scene_t* scene, const float* params, const float* t_frames,
                       int32_t Bt, const float* d_images, const float* e_saved,
                       const void* acts_saved, float* d_params, void* workspace,

@@ -118,7 +118,7 @@ static void* delta_ptr(char* ws, int impl, int pl, void* per_chunk) {
 // per-frame scratch of the backward beyond saved activations
 static size_t bwd_frame_bytes(const bhnerf_scene_t* sc, int impl, int pl) {
   return impl == BHNERF_IMPL_SIMT ? bh_simt_delta_floats_per_frame(sc->n_pad) * 4
-                                  : bh_tc_delta_bytes_per_frame(sc->n_pad, pl);
+                                  : bh_tc_delta_bytes_per_frame(sc->n_pad, pl) + (size_t)sc->n_pad * 4 /* d loss/d o */;
 }
 
 // TC variant needs scratch for the bf16 weight images; the SIMT variant ignores it.
@@ -182,6 +182,7 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
     int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
     char* q = p;
     float* delta = (float*)delta_ptr(ws, impl, pl, q); q += bwd_frame_bytes(sc, impl, pl) * nb;
+    float* dout = (float*)(q - (size_t)sc->n_pad * 4 * nb);       // tail of the per-frame scratch (TC family)
     const void* acts = acts_saved ? (const char*)acts_saved + acts_bytes_per_frame(sc, impl, pl) * b0 : nullptr;
     const float* e = e_saved ? e_saved + (size_t)b0 * sc->n_pad : nullptr;
     if (recompute) {
@@ -198,7 +199,7 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
     if (impl == BHNERF_IMPL_SIMT) {
       if (int r = bh_simt_bwd(v, params, dI, nb, e, (const float*)acts, delta, (float*)ws, d_params, st)) return r;
     } else {
-      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, delta, pl, d_params, st)) return r;
+      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, delta, dout, pl, d_params, st)) return r;
     }
   }
   return 0;
@@ -247,6 +248,7 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
     char* q = ws + fixed;
     void* acts = q; q += acts_bytes_per_frame(sc, impl, pl) * nb;
     float* delta = (float*)delta_ptr(ws, impl, pl, q); q += bwd_frame_bytes(sc, impl, pl) * nb;
+    float* dout = (float*)(q - (size_t)sc->n_pad * 4 * nb);
     float* e = (float*)q; q += (size_t)sc->n_pad * 4 * nb;
     float* dI = (float*)q;
     float* img = images + (size_t)b0 * sc->S * sc->P;
@@ -261,7 +263,7 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
     if (impl == BHNERF_IMPL_SIMT) {
       if (int r = bh_simt_bwd(v, params, dI, nb, e, (const float*)acts, delta, (float*)ws, d_params, st)) return r;
     } else {
-      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, delta, pl, d_params, st)) return r;
+      if (int r = bh_tc_bwd(v, ws, params, dI, nb, e, acts, delta, dout, pl, d_params, st)) return r;
     }
   }
   return 0;

@@ -151,5 +151,5 @@ int bh_tc_prepare_weights(const float* params, void* ws, cudaStream_t st);
 int bh_tc_fwd(const PackedView& v, const FrameConsts& fc, const void* ws, const float* params,
               const float* t_frames, int Bt, float* e_out, void* acts /*or null*/, int planes, cudaStream_t st);
 int bh_tc_bwd(const PackedView& v, const void* ws, const float* params, const float* d_images, int Bt,
-              const float* e_saved, const void* acts, void* delta_ws, int planes, float* d_params /*accumulated into*/,
-              cudaStream_t st);
+              const float* e_saved, const void* acts, void* delta_ws, float* dout_ws /*[Bt,n_pad], may alias e_saved*/,
+              int planes, float* d_params /*accumulated into*/, cudaStream_t st);

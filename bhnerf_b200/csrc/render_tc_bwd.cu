@@ -56,11 +56,28 @@ __device__ __forceinline__ void delta_pack(uint32_t h2, float a, float b, uint32
   if (PL == 2) lo = relu_mask2(h2, pack_bf16x2(a - bf16_lo(p), b - bf16_hi(p)));
 }
 
+// d loss / d o of every evaluated sample, once per backward, so that the dependent gathers (ray -> dI[ray]) are
+// off the dgrad chain:  dout = e(1-e) * sum_c dI[b,c,ray] * w[c,i]   (sigmoid', network.py:230; kgeo.py:621).
+// In place over e when the caller owns that buffer (dout == e is allowed: one thread reads and writes an element).
+__global__ void __launch_bounds__(256)
+tc_dout_kernel(PackedView v, const float* __restrict__ d_images, const float* e, int Bt, float* dout) {
+  const size_t n = (size_t)Bt * v.n_pad;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / v.n_pad), i = (int)(idx - (size_t)b * v.n_pad);
+    const int ray = v.ray[i];
+    float g = 0.f;
+    if (ray >= 0)
+      for (int c = 0; c < v.S; ++c) g += d_images[((size_t)b * v.S + c) * v.P + ray] * v.w[(size_t)c * v.n_pad + i];
+    const float ev = e[idx];
+    dout[idx] = g * ev * (1.f - ev);
+  }
+}
+
 template <int PL, bool FUSED>
 __device__ __forceinline__ void
 dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, const PackedView& v,
-           const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
-           const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
+           const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
+           const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
            float* __restrict__ d_params, int* __restrict__ status) {
   uint8_t* wsm = smem + D_SM_W;
   float* w4s = (float*)(smem + D_SM_W4);
@@ -144,13 +161,31 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
     bool ok = true;
     const size_t act_fs = tc_acts_bytes_per_frame(v.n_pad, PL), del_fs = tc_delta_bytes_per_frame(v.n_pad, PL);
     const size_t lstride = (size_t)v.n_pad * 256u, pstride = (size_t)v.n_pad * 1024u;
+    // fused: a finished tile is handed to the wgrad CTA with ONE release (MEMBAR.GPU: every store of the warp must
+    // have reached L2), issued while the warp would wait for the next tile's first MMA anyway
+    uint32_t pub_addr = 0u;
+    auto publish_pending = [&]() {
+      if (FUSED && pub_addr) {
+        fence_proxy_async_global();         // generic-proxy stores -> the partner's cp.async.bulk reads (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(pub_addr);
+        pub_addr = 0u;
+      }
+    };
+    // d loss / d o of this thread's sample (tc_dout_kernel), loaded one tile ahead
+    auto load_dout = [&](int r) -> float {
+      const int T = (r * ncta + cta) * 2 + slot;
+      if (T >= NT) return 0.f;
+      const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
+      return dout_all[(size_t)b * v.n_pad + tile * 128 + row];
+    };
+    float dout_next = load_dout(0);
     for (int r = 0; ok; ++r) {
       int T0 = (r * ncta + cta) * 2;
       if (T0 >= NT) break;
       int T = T0 + slot;
       if (T >= NT) continue;
       const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
-      const int i = tile * 128 + row;
       const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
       // delta images of this tile: the per-frame scratch, or (fused) tile set `rd` of the pair's ring
       const uint32_t rk = (uint32_t)(2 * r + slot), rd = rk % kRingDepth;
@@ -158,25 +193,12 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
       uint8_t* aux = FUSED ? del_tile + 4u * TC_SIMG_BYTES
                            : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
-      // tell the wgrad CTA that delta_l (and, with l = 3, the aux image) of this tile is in the ring
-      auto publish = [&](int l) {
-        if (FUSED) {
-          fence_proxy_async_global();       // generic-proxy stores -> the partner's cp.async.bulk reads (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(link.peer_bars + (rd * 4u + (uint32_t)l) * 8u);
-        }
-      };
       // ReLU masks of this row's 64 columns: the saved bf16 activations, loaded ahead of their use
       uint4 h[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) h[g] = *reinterpret_cast<const uint4*>(act_tile + 3 * lstride + sample_img_off(row, cg0 + g));
-      // d loss / d o = e(1-e) * sum_c dI[b,c,ray] * w[c,i]   (sigmoid', network.py:230; kgeo.py:621)
-      const int ray = v.ray[i];
-      const float e = e_saved[(size_t)b * v.n_pad + i];
-      float g = 0.f;
-      if (ray >= 0)
-        for (int c = 0; c < v.S; ++c) g += d_images[((size_t)b * v.S + c) * v.P + ray] * v.w[(size_t)c * v.n_pad + i];
-      const float dout = g * e * (1.f - e);
+      const float dout = dout_next;
+      dout_next = load_dout(r + 1);
       if (FUSED) {       // ring slot free: the partner has pulled tile rk - kRingDepth out of it
         ok = wait_cluster(&bars[DB_GFREE + rd], ((rk / kRingDepth) & 1u) ^ 1u, ab);
         if (!ok) break;
@@ -214,7 +236,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
-      publish(3);
+      publish_pending();                   // the previous tile of this slot (overlaps the MMA of delta_3)
       for (int l = 3; l >= 1; --l) {       // D = delta_l * W_l^T  ->  delta_{l-1}
         const uint8_t* h_img = act_tile + (size_t)(l - 1) * lstride;
         uint8_t* d_img = del_tile + (size_t)(l - 1) * dls;
@@ -256,9 +278,10 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
         }
-        publish(l - 1);
       }
+      if (FUSED) pub_addr = link.peer_bars + rd * 8u;      // handed over during the next tile (or after the loop)
     }
+    publish_pending();
     // d b4 = sum dout (network.py:64 bias of the last Dense)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) db4 += __shfl_xor_sync(0xffffffffu, db4, o);
@@ -273,11 +296,11 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 
 template <int PL>
 __global__ void __launch_bounds__(kDThreads, 1)
-tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
-                const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
+tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
+                const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
                 float* __restrict__ d_params, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  dgrad_role<PL, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, d_images, Bt, e_saved, acts,
+  dgrad_role<PL, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, dout_all, Bt, acts,
                         deltas, d_params, status);
 }
 
@@ -293,9 +316,9 @@ template <int PL> struct WCfg {
   static constexpr uint32_t SM_BARS = SM_FEAT + 2 * W_FBUF;
   static constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 };
-// WB_GFULL[d][l]: delta_l (l = 3 also: aux) of the tile in ring set d is written; 8 remote arrivals (the dgrad
-// CTA's epilogue warps of that slot) per phase
-enum { WB_FULL = 0, WB_EMPTY = 3, WB_FFULL = 6, WB_FEMPTY = 8, WB_DONE = 10, WB_GFULL = 11, WB_NBARS = 11 + 4 * kRingDepth };
+// WB_GFULL[d]: the four delta images and the aux image of the tile in ring set d are written; 8 remote arrivals
+// (the dgrad CTA's epilogue warps of that slot) per phase
+enum { WB_FULL = 0, WB_EMPTY = 3, WB_FFULL = 6, WB_FEMPTY = 8, WB_DONE = 10, WB_GFULL = 11, WB_NBARS = 11 + kRingDepth };
 static_assert(WB_NBARS * 8 + 16 <= 256, "wgrad barrier area");
 // TMEM accumulator columns (lane = n, or j for dW4)
 constexpr uint32_t ACC_W3 = 0, ACC_W3F = 128, ACC_W2 = 160, ACC_W1 = 288, ACC_W0F = 416, ACC_B2 = 448, ACC_B1 = 464,
@@ -346,7 +369,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
     for (int s = 0; s < kWStages; ++s) { mbar_init(&bars[WB_FULL + s], 1); mbar_init(&bars[WB_EMPTY + s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bars[WB_FFULL + s], 1); mbar_init(&bars[WB_FEMPTY + s], 1); }
     mbar_init(&bars[WB_DONE], 1);
-    for (int s = 0; s < 4 * kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], 8);
+    for (int s = 0; s < kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], 8);
     *abort_s = 0;
     mbar_fence_init();
   }
@@ -387,8 +410,8 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
           mbar_expect_tx(&bars[WB_FFULL + fs], PL * TC_FIMG_BYTES + TC_AIMG_BYTES);
           bulk_g2s(dst, fsrc, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
           if (PL == 2) bulk_g2s(dst + TC_FIMG_BYTES, fsrc + (size_t)n_pad * 64u, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
-          if (FUSED) {      // aux is published together with delta_3
-            ok = wait_cluster(&bars[WB_GFULL + rd * 4u + 3u], ru, ab);
+          if (FUSED) {      // the dgrad CTA has written this tile's delta / aux images into ring set rd
+            ok = wait_cluster(&bars[WB_GFULL + rd], ru, ab);
             if (!ok) break;
             fence_proxy_async_global();
           }
@@ -401,11 +424,6 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
           uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
           ok = wait(&bars[WB_EMPTY + st], ph ^ 1u, ab);
           if (!ok) break;
-          if (FUSED && j < 4) {       // delta_{3-j} of this tile has left the dgrad CTA
-            ok = wait_cluster(&bars[WB_GFULL + rd * 4u + (uint32_t)(3 - j)], ru, ab);
-            if (!ok) break;
-            fence_proxy_async_global();
-          }
           uint8_t* dst = smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES;
           const uint8_t* a_src = (j < 4) ? del_tile + pa * pstride + (size_t)(3 - j) * dls
                                          : act_tile + pa * pstride + 3 * lstride;
@@ -537,8 +555,8 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
 constexpr uint32_t F_SM_TOTAL = D_SM_TOTAL > WCfg<1>::SM_TOTAL ? D_SM_TOTAL : WCfg<1>::SM_TOTAL;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
-tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ d_images, int Bt,
-                    const float* __restrict__ e_saved, const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
+tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
+                    const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
                     float* __restrict__ d_params, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t rank = cluster_ctarank();
@@ -547,7 +565,7 @@ tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* _
   link.ring = ring + (size_t)pair * kRingDepth * TSET_BYTES;
   if (rank == 0) {
     link.peer_bars = mapa_u32(smem_u32(smem + WCfg<1>::SM_BARS + WB_GFULL * 8), 1u);
-    dgrad_role<1, true>(smem, pair, npairs, link, v, ws, d_images, Bt, e_saved, acts, nullptr, d_params, status);
+    dgrad_role<1, true>(smem, pair, npairs, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
   } else {
     link.peer_bars = mapa_u32(smem_u32(smem + D_SM_BARS + DB_GFREE * 8), 0u);
     wgrad_role<1, true>(smem, pair, npairs, link, v.n_pad, Bt, acts, nullptr, d_params, status);
@@ -572,14 +590,21 @@ bool bwd_fused_enabled() {                 // BHNERF_TC_FUSED=0 selects the two-
 
 template <int PL>
 int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int Bt, const float* e_saved, const void* acts,
-               void* delta_ws, float* d_params, cudaStream_t st) {
+               void* delta_ws, float* dout, float* d_params, cudaStream_t st) {
   int* status = (int*)((uint8_t*)ws + TC_WS_STATUS);
   const int NT = Bt * (v.n_pad / 128);
+  {
+    BhProfScope ps(BH_CAT_HEADS, 1, st);
+    size_t n = (size_t)Bt * v.n_pad;
+    int grid = (int)((n + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    tc_dout_kernel<<<grid, 256, 0, st>>>(v, d_images, e_saved, Bt, dout);
+    BH_CHECK_CUDA(cudaGetLastError());
+  }
   if (PL == 1 && bwd_fused_enabled()) {
     BhProfScope ps(BH_CAT_BWD, 1, st);
     BH_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SM_TOTAL));
     int npairs = (NT + 1) / 2; if (npairs > num_sms_b() / 2) npairs = num_sms_b() / 2;
-    tc_bwd_fused_kernel<<<2 * npairs, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, d_images, Bt, e_saved,
+    tc_bwd_fused_kernel<<<2 * npairs, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt,
                                                                  (const uint8_t*)acts, (uint8_t*)delta_ws, d_params, status);
     BH_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -588,7 +613,7 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
     BhProfScope ps(BH_CAT_BWD, 1, st);
     BH_CHECK_CUDA(cudaFuncSetAttribute(tc_dgrad_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SM_TOTAL));
     int grid = (NT + 1) / 2; if (grid > num_sms_b()) grid = num_sms_b();
-    tc_dgrad_kernel<PL><<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, d_images, Bt, e_saved,
+    tc_dgrad_kernel<PL><<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt,
                                                              (const uint8_t*)acts, (uint8_t*)delta_ws, d_params, status);
     BH_CHECK_CUDA(cudaGetLastError());
   }
@@ -615,9 +640,10 @@ size_t bh_tc_delta_fixed_bytes(int planes) {
 }
 
 int bh_tc_bwd(const PackedView& v, const void* ws, const float* params, const float* d_images, int Bt,
-              const float* e_saved, const void* acts, void* delta_ws, int planes, float* d_params, cudaStream_t st) {
+              const float* e_saved, const void* acts, void* delta_ws, float* dout_ws, int planes, float* d_params,
+              cudaStream_t st) {
   (void)params;
-  if (!e_saved || !acts || !delta_ws) { bh_set_error("bh_tc_bwd: saved e / activations / delta scratch required"); return 1; }
-  return planes == 2 ? launch_bwd<2>(v, ws, d_images, Bt, e_saved, acts, delta_ws, d_params, st)
-                     : launch_bwd<1>(v, ws, d_images, Bt, e_saved, acts, delta_ws, d_params, st);
+  if (!e_saved || !acts || !delta_ws || !dout_ws) { bh_set_error("bh_tc_bwd: saved e / activations / delta + dout scratch required"); return 1; }
+  return planes == 2 ? launch_bwd<2>(v, ws, d_images, Bt, e_saved, acts, delta_ws, dout_ws, d_params, st)
+                     : launch_bwd<1>(v, ws, d_images, Bt, e_saved, acts, delta_ws, dout_ws, d_params, st);
 }

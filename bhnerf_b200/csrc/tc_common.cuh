@@ -77,6 +77,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// pull `bytes` (multiple of 16) of global memory into L2 ahead of their use; one instruction, no destination
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ uint32_t sample_img_off(int row, int colgroup) {   // 16-byte chunk of 8 columns
   return (uint32_t)(row >> 3) * TC_IMG_RS + (uint32_t)colgroup * TC_SIMG_CS + (uint32_t)(row & 7) * 16u;
 }

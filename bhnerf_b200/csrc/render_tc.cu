@@ -19,22 +19,6 @@
 
 using namespace tc;
 
-// Optional cycle accounting (-DBH_TC_TIMING): block 0 writes, per role, the cycles spent waiting vs working into
-// the workspace status words [8..20) (two int32 per counter).  Compiled out by default.
-#ifdef BH_TC_TIMING
-#define BH_TIMING_DECL(v) long long v = 0; long long _t0_##v = 0; (void)_t0_##v;
-#define BH_TIMING_BEGIN _bh_t0 = clock64();
-#define BH_TIMING_END(v) v += clock64() - _bh_t0;
-#define BH_TIMING_T0 long long _bh_t0 = 0;
-#define BH_TIMING_STORE(st, i, v) if (blockIdx.x == 0) { (st)[i] = (int)(v & 0xffffffffll); (st)[(i) + 1] = (int)(v >> 32); }
-#else
-#define BH_TIMING_T0
-#define BH_TIMING_DECL(v)
-#define BH_TIMING_BEGIN
-#define BH_TIMING_END(v)
-#define BH_TIMING_STORE(st, i, v)
-#endif
-
 namespace {
 
 constexpr int kThreads = 576;            // 16 epilogue warps + MMA issuer + weight producer
@@ -394,6 +378,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
         uint8_t* act_img = SAVE ? act_tile + (size_t)l * ((size_t)v.n_pad * 256u) : nullptr;
         // this warp's 64 columns: both TMEM loads in flight before the first use
         uint32_t raw[2][32];
+        uint32_t mword[2] = {0u, 0u};                   // relu bit masks of this thread's 64 columns (backward)
         tmem_ld32(t_lane + (uint32_t)(half * 64), raw[0]);
         tmem_ld32(t_lane + (uint32_t)(half * 64 + 32), raw[1]);
         tmem_wait_ld();
@@ -422,6 +407,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               hi[j] = pack_bf16x2_rn_relu(x[2 * j], x[2 * j + 1]);
+              mword[cc] |= tc_mask_bits(hi[j], j);
               if (SAVE == 2)
                 lo[j] = pack_bf16x2(fmaxf(x[2 * j], 0.f) - bf16_lo(hi[j]), fmaxf(x[2 * j + 1], 0.f) - bf16_hi(hi[j]));
             }
@@ -441,6 +427,9 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[BAR_AREADY + slot]);
         }
+        if (SAVE)
+          *reinterpret_cast<uint2*>(acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + tc_mask_off(v.n_pad, SAVE) +
+                                    tc_mask_word_off(tile, l, half, row)) = make_uint2(mword[0], mword[1]);
         BH_TIMING_END(t_ep)
       }
       if (!ok) break;

@@ -43,17 +43,17 @@ struct PairLink {
   uint32_t peer_bars;     // shared::cluster address of the partner's link barriers (wgrad: GFULL[d][l]; dgrad: GFREE[d])
 };
 
-__device__ __forceinline__ uint32_t relu_mask2(uint32_t h2, uint32_t d2) {   // keep the bf16 halves of d2 where h2 > 0
-  uint32_t m = ((h2 & 0x00007fffu) ? 0x0000ffffu : 0u) | ((h2 & 0x7fff0000u) ? 0xffff0000u : 0u);
-  return d2 & m;
-}
-
-// split two fp32 cotangents into packed bf16 hi / lo words and apply the relu mask of the packed activations h2
+#ifdef BH_EXP_NOSTG        // timing experiment: the delta images are not written (wrong results)
+#define BH_DSTORE(p, v) do { if (((size_t)(p) & 1u)) *reinterpret_cast<uint4*>(p) = (v); } while (0)
+#else
+#define BH_DSTORE(p, v) (*reinterpret_cast<uint4*>(p) = (v))
+#endif
+// split two fp32 cotangents into packed bf16 hi / lo words and apply the relu mask m (0xffff per surviving half)
 template <int PL>
-__device__ __forceinline__ void delta_pack(uint32_t h2, float a, float b, uint32_t& hi, uint32_t& lo) {
+__device__ __forceinline__ void delta_pack(uint32_t m, float a, float b, uint32_t& hi, uint32_t& lo) {
   uint32_t p = pack_bf16x2(a, b);
-  hi = relu_mask2(h2, p);
-  if (PL == 2) lo = relu_mask2(h2, pack_bf16x2(a - bf16_lo(p), b - bf16_hi(p)));
+  hi = p & m;
+  if (PL == 2) lo = pack_bf16x2(a - bf16_lo(p), b - bf16_hi(p)) & m;
 }
 
 // d loss / d o of every evaluated sample, once per backward, so that the dependent gathers (ray -> dI[ray]) are
@@ -118,6 +118,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
     {   // whole warp runs the loop; elect.sync inside the issue wrappers picks the issuing lane
       const uint32_t idesc = make_idesc(128, 128, 0, 0);      // A from TMEM, B K-major
       uint32_t a_phase[2] = {0u, 0u};
+      BH_TIMING_T0 BH_TIMING_DECL(t_wa) BH_TIMING_DECL(t_is)
       bool ok = wait(&bars[DB_WFULL], 0, ab);
       for (int r = 0; ok; ++r) {
         int T0 = (r * ncta + cta) * 2;
@@ -127,11 +128,14 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           const uint32_t plane = tc_plane_bytes(l), cs = (tc_layer_K(l) / 8u) * 128u;
           for (int s = 0; s < 2; ++s) {
             if (T0 + s >= NT) continue;
+            BH_TIMING_BEGIN
             ok = wait(&bars[DB_AREADY + s], a_phase[s], ab);
+            BH_TIMING_END(t_wa)
             if (!ok) break;
             a_phase[s] ^= 1u;
             tc_fence_after_sync();
             const uint32_t td = tbase + (uint32_t)s * 256u, ta = td + 128u;
+            BH_TIMING_BEGIN
             if (elect_one()) {
               // B' [K'=n][N'=k] = W_l[k][n]: the forward-layout image read K-major (K' groups = column groups);
               // passes: d_hi*W_hi, d_hi*W_lo, and with both planes d_lo*W_hi.  Unrolled, descriptor halves precomputed.
@@ -146,9 +150,11 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
               mma_commit_raw(&bars[DB_DREADY + s]);
             }
             __syncwarp();
+            BH_TIMING_END(t_is)
           }
         }
       }
+      if (lane == 0) { BH_TIMING_STORE(status, 20, t_wa) BH_TIMING_STORE(status, 22, t_is) }
     }
     __syncwarp();
   } else {
@@ -166,7 +172,9 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
     uint32_t pub_addr = 0u;
     auto publish_pending = [&]() {
       if (FUSED && pub_addr) {
+#ifndef BH_EXP_NOFENCE
         fence_proxy_async_global();         // generic-proxy stores -> the partner's cp.async.bulk reads (async proxy)
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(pub_addr);
         pub_addr = 0u;
@@ -180,29 +188,46 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       return dout_all[(size_t)b * v.n_pad + tile * 128 + row];
     };
     float dout_next = load_dout(0);
+    uint2 mk_next[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+    auto load_masks = [&](int r) {
+      const int T = (r * ncta + cta) * 2 + slot;
+      if (T >= NT) return;
+      const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
+      const uint8_t* mbase = acts + (size_t)b * act_fs + tc_mask_off(v.n_pad, PL);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) mk_next[l] = *reinterpret_cast<const uint2*>(mbase + tc_mask_word_off(tile, l, half, row));
+    };
+    load_masks(0);
+    BH_TIMING_T0 BH_TIMING_DECL(t_top) BH_TIMING_DECL(t_gf) BH_TIMING_DECL(t_pub) BH_TIMING_DECL(t_wd) BH_TIMING_DECL(t_ep)
+#ifdef BH_TC_TIMING
+    const long long t_loop0 = clock64();
+#endif
     for (int r = 0; ok; ++r) {
       int T0 = (r * ncta + cta) * 2;
       if (T0 >= NT) break;
       int T = T0 + slot;
       if (T >= NT) continue;
       const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
-      const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
       // delta images of this tile: the per-frame scratch, or (fused) tile set `rd` of the pair's ring
       const uint32_t rk = (uint32_t)(2 * r + slot), rd = rk % kRingDepth;
       uint8_t* del_tile = FUSED ? link.ring + (size_t)rd * TSET_BYTES : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
       const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
       uint8_t* aux = FUSED ? del_tile + 4u * TC_SIMG_BYTES
                            : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
-      // ReLU masks of this row's 64 columns: the saved bf16 activations, loaded ahead of their use
-      uint4 h[8];
+      // ReLU bit masks of this row's 64 columns, all four layers (loaded one tile ahead, like dout)
+      uint2 mk[4];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) h[g] = *reinterpret_cast<const uint4*>(act_tile + 3 * lstride + sample_img_off(row, cg0 + g));
+      for (int l = 0; l < 4; ++l) mk[l] = mk_next[l];
       const float dout = dout_next;
       dout_next = load_dout(r + 1);
+      load_masks(r + 1);
       if (FUSED) {       // ring slot free: the partner has pulled tile rk - kRingDepth out of it
+        BH_TIMING_BEGIN
         ok = wait_cluster(&bars[DB_GFREE + rd], ((rk / kRingDepth) & 1u) ^ 1u, ab);
+        BH_TIMING_END(t_gf)
         if (!ok) break;
       }
+      BH_TIMING_BEGIN
       if (half == 0) {
         db4 += dout;
         // aux image [128][16]: col 0 = bf16 hi part of dout, col 1 = lo part
@@ -217,14 +242,13 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
           const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
-          const uint4 hh = h[4 * cc + gq];
+          const uint32_t mw = cc ? mk[3].y : mk[3].x;
           const float* w4 = w4s + (cg0 + 4 * cc + gq) * 8;
-          delta_pack<PL>(hh.x, dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
-          delta_pack<PL>(hh.y, dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
-          delta_pack<PL>(hh.z, dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
-          delta_pack<PL>(hh.w, dout * w4[6], dout * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
-          *reinterpret_cast<uint4*>(del_tile + 3 * dls + off) =
-              make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 3), dout * w4[6], dout * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
+          BH_DSTORE(del_tile + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
           if (PL == 2)
             *reinterpret_cast<uint4*>(del_tile + pstride + 3 * dls + off) =
                 make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
@@ -236,16 +260,20 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
+      BH_TIMING_END(t_top)
+      BH_TIMING_BEGIN
       publish_pending();                   // the previous tile of this slot (overlaps the MMA of delta_3)
+      BH_TIMING_END(t_pub)
       for (int l = 3; l >= 1; --l) {       // D = delta_l * W_l^T  ->  delta_{l-1}
-        const uint8_t* h_img = act_tile + (size_t)(l - 1) * lstride;
         uint8_t* d_img = del_tile + (size_t)(l - 1) * dls;
-#pragma unroll
-        for (int gI = 0; gI < 8; ++gI) h[gI] = *reinterpret_cast<const uint4*>(h_img + sample_img_off(row, cg0 + gI));
+        const uint2 mkl = l == 3 ? mk[2] : (l == 2 ? mk[1] : mk[0]);
+        BH_TIMING_BEGIN
         ok = wait(&bars[DB_DREADY + slot], d_phase, ab);
+        BH_TIMING_END(t_wd)
         if (!ok) break;
         d_phase ^= 1u;
         tc_fence_after_sync();
+        BH_TIMING_BEGIN
         uint32_t raw[2][32];
         tmem_ld32(t_lane + (uint32_t)(half * 64), raw[0]);
         tmem_ld32(t_lane + (uint32_t)(half * 64 + 32), raw[1]);
@@ -256,13 +284,13 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
-            const uint4 hh = h[4 * cc + gq];
+            const uint32_t mw = cc ? mkl.y : mkl.x;
             const uint32_t* rr = raw[cc] + 8 * gq;
-            delta_pack<PL>(hh.x, __uint_as_float(rr[0]), __uint_as_float(rr[1]), d[4 * gq + 0], dl[4 * gq + 0]);
-            delta_pack<PL>(hh.y, __uint_as_float(rr[2]), __uint_as_float(rr[3]), d[4 * gq + 1], dl[4 * gq + 1]);
-            delta_pack<PL>(hh.z, __uint_as_float(rr[4]), __uint_as_float(rr[5]), d[4 * gq + 2], dl[4 * gq + 2]);
-            delta_pack<PL>(hh.w, __uint_as_float(rr[6]), __uint_as_float(rr[7]), d[4 * gq + 3], dl[4 * gq + 3]);
-            *reinterpret_cast<uint4*>(d_img + off) = make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]);
+            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), __uint_as_float(rr[0]), __uint_as_float(rr[1]), d[4 * gq + 0], dl[4 * gq + 0]);
+            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), __uint_as_float(rr[2]), __uint_as_float(rr[3]), d[4 * gq + 1], dl[4 * gq + 1]);
+            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), __uint_as_float(rr[4]), __uint_as_float(rr[5]), d[4 * gq + 2], dl[4 * gq + 2]);
+            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 3), __uint_as_float(rr[6]), __uint_as_float(rr[7]), d[4 * gq + 3], dl[4 * gq + 3]);
+            BH_DSTORE(d_img + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
             if (PL == 2)
               *reinterpret_cast<uint4*>(d_img + pstride + off) =
                   make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
@@ -278,10 +306,18 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[DB_AREADY + slot]);
         }
+        BH_TIMING_END(t_ep)
       }
       if (FUSED) pub_addr = link.peer_bars + rd * 8u;      // handed over during the next tile (or after the loop)
     }
     publish_pending();
+#ifdef BH_TC_TIMING
+    if (tid == 0) {
+      long long t_loop = clock64() - t_loop0;
+      BH_TIMING_STORE(status, 24, t_top) BH_TIMING_STORE(status, 26, t_gf) BH_TIMING_STORE(status, 28, t_pub)
+      BH_TIMING_STORE(status, 30, t_wd) BH_TIMING_STORE(status, 32, t_ep) BH_TIMING_STORE(status, 34, t_loop)
+    }
+#endif
     // d b4 = sum dout (network.py:64 bias of the last Dense)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) db4 += __shfl_xor_sync(0xffffffffu, db4, o);
@@ -308,25 +344,30 @@ tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __res
 // wgrad
 // =====================================================================================================
 constexpr int kWThreads = 192;             // warps 0-3 final epilogue, warp 4 MMA issuer, warp 5 producer
-constexpr uint32_t W_SM_STAGE = 0;                                            // kWStages x [A 32K | B 32K]
+// One stage of the operand ring = the A image, the B image and the slice of the feature image that rides on the same
+// MMA as extra N columns: [A 32K | B 32K | F 8K].  Small-N MMAs cost as much as N=128 ones in SS form (the A read
+// from shared memory dominates: measured ~105 cycles per MMA for any N <= 128), so the skip/bias products are
+// appended to the big ones (N = 160 / 144) instead of being issued on their own.
+constexpr uint32_t W_STAGE_BYTES = 2u * TC_SIMG_BYTES + TC_FIMG_BYTES;
 template <int PL> struct WCfg {
   static constexpr int kWStages = PL == 2 ? 2 : 3;                            // the two-plane plan is for small steps
-  static constexpr uint32_t W_FBUF = PL * TC_FIMG_BYTES + TC_AIMG_BYTES;      // [feat hi 8K | (feat lo 8K) | aux 4K]
-  static constexpr uint32_t SM_FEAT = kWStages * 2 * TC_SIMG_BYTES;           // 2 x W_FBUF
-  static constexpr uint32_t SM_BARS = SM_FEAT + 2 * W_FBUF;
+  static constexpr uint32_t SM_BARS = kWStages * W_STAGE_BYTES;
   static constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 };
 // WB_GFULL[d]: the four delta images and the aux image of the tile in ring set d are written; 8 remote arrivals
 // (the dgrad CTA's epilogue warps of that slot) per phase
-enum { WB_FULL = 0, WB_EMPTY = 3, WB_FFULL = 6, WB_FEMPTY = 8, WB_DONE = 10, WB_GFULL = 11, WB_NBARS = 11 + kRingDepth };
+enum { WB_FULL = 0, WB_EMPTY = 3, WB_DONE = 10, WB_GFULL = 11, WB_NBARS = 11 + kRingDepth };
 static_assert(WB_NBARS * 8 + 16 <= 256, "wgrad barrier area");
-// TMEM accumulator columns (lane = n, or j for dW4)
-constexpr uint32_t ACC_W3 = 0, ACC_W3F = 128, ACC_W2 = 160, ACC_W1 = 288, ACC_W0F = 416, ACC_B2 = 448, ACC_B1 = 464,
+// TMEM accumulator columns (lane = n, or j for dW4): [dW3 128 | dW3 skip rows + b3 32] [dW2 128 | b2 16]
+// [dW1 128 | b1 16] [dW0 + b0 32] [dW4 16]
+constexpr uint32_t ACC_W3 = 0, ACC_W3F = 128, ACC_W2 = 160, ACC_B2 = 288, ACC_W1 = 304, ACC_B1 = 432, ACC_W0F = 448,
                    ACC_W4 = 480;
 
 // Per tile the CTA runs a list of stage fills ("sub-jobs").  job j picks the operands
-//   0: delta_3 x h2 (+feat)   1: delta_2 x h1 (+ones)   2: delta_1 x h0 (+ones)   3: delta_0 x feat   4: h3 x aux
-// and with two planes every job runs its bf16 plane combinations (A plane pa, B plane pb):
+//   0: delta_3 x [h2 | feat]   1: delta_2 x [h1 | feat cols 16..31]   2: delta_1 x [h0 | feat cols 16..31]
+//   3: delta_0 x feat          4: h3 x aux
+// (feature column 21 is the constant one: bias gradients) and with two planes every job runs its bf16 plane
+// combinations (A plane pa, B plane pb):
 //   jobs 0-3: (hi,hi) (lo,hi) (hi,lo)      job 4: (hi,-) (lo,-)   [aux carries both parts of dout]
 template <int PL> __device__ __forceinline__ int wg_num_subjobs() { return PL == 2 ? 14 : 5; }
 template <int PL> __device__ __forceinline__ void wg_subjob(int idx, int& j, int& pa, int& pb) {
@@ -354,7 +395,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
            int* __restrict__ status) {
   static_assert(!(FUSED && PL == 2), "the fused pair runs the one-plane plan");
   constexpr int kWStages = WCfg<PL>::kWStages;
-  constexpr uint32_t W_SM_FEAT = WCfg<PL>::SM_FEAT, W_SM_BARS = WCfg<PL>::SM_BARS, W_FBUF = WCfg<PL>::W_FBUF;
+  constexpr uint32_t W_SM_BARS = WCfg<PL>::SM_BARS;
   uint64_t* bars = (uint64_t*)(smem + W_SM_BARS);
   uint32_t* tmem_base_s = (uint32_t*)(bars + WB_NBARS);
   int* abort_s = (int*)(tmem_base_s + 1);
@@ -367,7 +408,6 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
 
   if (tid == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(&bars[WB_FULL + s], 1); mbar_init(&bars[WB_EMPTY + s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars[WB_FFULL + s], 1); mbar_init(&bars[WB_FEMPTY + s], 1); }
     mbar_init(&bars[WB_DONE], 1);
     for (int s = 0; s < kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], 8);
     *abort_s = 0;
@@ -385,8 +425,9 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
   if (warp == 5) {
     // ===================== producer: bulk copies of the saved images =====================
     if (lane == 0) {
-      uint32_t cnt = 0, fcnt = 0;
+      uint32_t cnt = 0;
       bool ok = true;
+      BH_TIMING_T0 BH_TIMING_DECL(t_gfl) BH_TIMING_DECL(t_em)
       for (int it = 0; ok; ++it) {
         int T;
         const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
@@ -394,6 +435,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
         if (tv == 2) continue;
         const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
         const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
+        const uint8_t* feat_tile = acts + (size_t)b * act_fs + pstride * PL + (size_t)tile * TC_FIMG_BYTES;
         // fused: ring set rd; use number ru of that set selects the barrier phase
         const uint32_t rd = (uint32_t)it % kRingDepth, ru = ((uint32_t)it / kRingDepth) & 1u;
         const uint8_t* del_tile = FUSED ? link.ring + (size_t)rd * TSET_BYTES
@@ -401,107 +443,106 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
         const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;
         const uint8_t* aux_src = FUSED ? del_tile + 4u * TC_SIMG_BYTES
                                        : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
-        {   // feature (+ lo plane) and aux images of this tile
-          uint32_t fs = fcnt & 1u;
-          ok = wait(&bars[WB_FEMPTY + fs], ((fcnt >> 1) & 1u) ^ 1u, ab);
+        if (FUSED) {      // the dgrad CTA has written this tile's delta / aux images into ring set rd
+          BH_TIMING_BEGIN
+          ok = wait_cluster(&bars[WB_GFULL + rd], ru, ab);
+          BH_TIMING_END(t_gfl)
           if (!ok) break;
-          uint8_t* dst = smem + W_SM_FEAT + fs * W_FBUF;
-          const uint8_t* fsrc = acts + (size_t)b * act_fs + pstride * PL + (size_t)tile * TC_FIMG_BYTES;
-          mbar_expect_tx(&bars[WB_FFULL + fs], PL * TC_FIMG_BYTES + TC_AIMG_BYTES);
-          bulk_g2s(dst, fsrc, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
-          if (PL == 2) bulk_g2s(dst + TC_FIMG_BYTES, fsrc + (size_t)n_pad * 64u, TC_FIMG_BYTES, &bars[WB_FFULL + fs]);
-          if (FUSED) {      // the dgrad CTA has written this tile's delta / aux images into ring set rd
-            ok = wait_cluster(&bars[WB_GFULL + rd], ru, ab);
-            if (!ok) break;
-            fence_proxy_async_global();
-          }
-          bulk_g2s(dst + PL * TC_FIMG_BYTES, aux_src, TC_AIMG_BYTES, &bars[WB_FFULL + fs]);
-          ++fcnt;
+          fence_proxy_async_global();
         }
         for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
           int j, pa, pb;
           wg_subjob<PL>(idx, j, pa, pb);
           uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
+          BH_TIMING_BEGIN
           ok = wait(&bars[WB_EMPTY + st], ph ^ 1u, ab);
+          BH_TIMING_END(t_em)
           if (!ok) break;
-          uint8_t* dst = smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES;
+          uint8_t* dst = smem + st * W_STAGE_BYTES;
+          uint64_t* full = &bars[WB_FULL + st];
           const uint8_t* a_src = (j < 4) ? del_tile + pa * pstride + (size_t)(3 - j) * dls
                                          : act_tile + pa * pstride + 3 * lstride;
-          mbar_expect_tx(&bars[WB_FULL + st], (j < 3) ? 2 * TC_SIMG_BYTES : TC_SIMG_BYTES);
-          bulk_g2s(dst, a_src, TC_SIMG_BYTES, &bars[WB_FULL + st]);
-          if (j < 3)
-            bulk_g2s(dst + TC_SIMG_BYTES, act_tile + pb * pstride + (size_t)(2 - j) * lstride, TC_SIMG_BYTES,
-                     &bars[WB_FULL + st]);
+          const uint8_t* f_src = feat_tile + (size_t)pb * ((size_t)n_pad * 64u);
+          const uint32_t b_bytes = (j == 0) ? TC_SIMG_BYTES + TC_FIMG_BYTES
+                                 : (j < 3) ? TC_SIMG_BYTES + TC_FIMG_BYTES / 2u
+                                 : (j == 3) ? TC_FIMG_BYTES : TC_AIMG_BYTES;
+          mbar_expect_tx(full, TC_SIMG_BYTES + b_bytes);
+          bulk_g2s(dst, a_src, TC_SIMG_BYTES, full);
+          uint8_t* bdst = dst + TC_SIMG_BYTES;
+          if (j < 3) {
+            bulk_g2s(bdst, act_tile + pb * pstride + (size_t)(2 - j) * lstride, TC_SIMG_BYTES, full);
+            if (j == 0) bulk_g2s(bdst + TC_SIMG_BYTES, f_src, TC_FIMG_BYTES, full);
+            else bulk_g2s(bdst + TC_SIMG_BYTES, f_src + TC_FIMG_BYTES / 2u, TC_FIMG_BYTES / 2u, full);    // cols 16..31
+          } else if (j == 3) {
+            bulk_g2s(bdst, f_src, TC_FIMG_BYTES, full);
+          } else {
+            bulk_g2s(bdst, aux_src, TC_AIMG_BYTES, full);
+          }
         }
       }
+      BH_TIMING_STORE_B(status, 38, t_gfl, FUSED ? 1 : 0) BH_TIMING_STORE_B(status, 40, t_em, FUSED ? 1 : 0)
     }
     __syncwarp();
   } else if (warp == 4) {
     // ===================== MMA issuer (whole warp, elect.sync inside the issue wrappers) =====================
     {
-      const uint32_t id128 = make_idesc(128, 128, 1, 1), id32 = make_idesc(128, 32, 1, 1), id16 = make_idesc(128, 16, 1, 1);
-      uint32_t cnt = 0, fcnt = 0;
+      const uint32_t id160 = make_idesc(128, 160, 1, 1), id144 = make_idesc(128, 144, 1, 1),
+                     id32 = make_idesc(128, 32, 1, 1), id16 = make_idesc(128, 16, 1, 1);
+      uint32_t cnt = 0;
       bool ok = true;
       uint32_t later_tile = 0;               // 0 for the CTA's first tile: accumulators start from zero
+      BH_TIMING_T0 BH_TIMING_DECL(t_fu) BH_TIMING_DECL(t_wi)
+#ifdef BH_TC_TIMING
+      const long long t_w0 = clock64();
+#endif
       // all operands are [s][c] images read MN-major: K (= sample) groups advance by RS, M/N groups by CS
       for (int it = 0; ok; ++it) {
         int T;
         const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
         if (tv == 0) break;
         if (tv == 2) continue;
-        uint32_t fs = fcnt & 1u;
-        ok = wait(&bars[WB_FFULL + fs], (fcnt >> 1) & 1u, ab);
-        if (!ok) break;
-        const uint32_t fbuf = smem_u32(smem + W_SM_FEAT + fs * W_FBUF);
-        const uint32_t aux = fbuf + PL * TC_FIMG_BYTES;
         for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
           int j, pa, pb;
           wg_subjob<PL>(idx, j, pa, pb);
           uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
+          BH_TIMING_BEGIN
           ok = wait(&bars[WB_FULL + st], ph, ab);
+          BH_TIMING_END(t_fu)
           if (!ok) break;
           tc_fence_after_sync();
-          // fused: delta_0 is the last image pulled out of the ring set -> hand the set back to the dgrad CTA
-          if (FUSED && j == 3) {
+          BH_TIMING_BEGIN
+          // fused: the aux image (job 4) is the last thing pulled out of the ring set -> hand the set back to the
+          // dgrad CTA
+          if (FUSED && j == 4) {
             if (elect_one()) mbar_arrive_remote(link.peer_bars + ((uint32_t)it % kRingDepth) * 8u);
             __syncwarp();
           }
-          const uint32_t A = smem_u32(smem + W_SM_STAGE + st * 2 * TC_SIMG_BYTES), B = A + TC_SIMG_BYTES;
-          const uint32_t feat = fbuf + (uint32_t)pb * TC_FIMG_BYTES;
+          const uint32_t A = smem_u32(smem + st * W_STAGE_BYTES), B = A + TC_SIMG_BYTES;
           const uint32_t started = later_tile | ((pa | pb) ? 1u : 0u);     // (hi,hi) is each accumulator's first product
+          const uint32_t acc_col = j == 0 ? ACC_W3 : j == 1 ? ACC_W2 : j == 2 ? ACC_W1 : j == 3 ? ACC_W0F : ACC_W4;
+          const uint32_t idesc = j == 0 ? id160 : j < 3 ? id144 : j == 3 ? id32 : id16;
           if (elect_one()) {
-            // all operands are [s][c] images read MN-major: K (= sample) groups advance by RS (LBO), M/N groups by CS (SBO)
             const uint32_t hi = desc_hi(TC_SIMG_CS), kstep = (2u * TC_IMG_RS) >> 4;
-            const uint32_t a_lo = desc_lo(A, TC_IMG_RS), b_lo = desc_lo(B, TC_IMG_RS), f_lo = desc_lo(feat, TC_IMG_RS);
-            const uint32_t o_lo = desc_lo(fbuf + 2u * TC_SIMG_CS, TC_IMG_RS), x_lo = desc_lo(aux, TC_IMG_RS);
+            const uint32_t a_lo = desc_lo(A, TC_IMG_RS), b_lo = desc_lo(B, TC_IMG_RS);
 #pragma unroll
-            for (uint32_t ks = 0; ks < 8; ++ks) {
-              const uint32_t acc = started | (ks > 0 ? 1u : 0u);
-              const uint32_t al = a_lo + ks * kstep;
-              if (j == 0) {
-                mma_ss_raw(tbase + ACC_W3, al, hi, b_lo + ks * kstep, hi, id128, acc);
-                mma_ss_raw(tbase + ACC_W3F, al, hi, f_lo + ks * kstep, hi, id32, acc);
-              } else if (j == 1) {
-                mma_ss_raw(tbase + ACC_W2, al, hi, b_lo + ks * kstep, hi, id128, acc);
-                if (pb == 0) mma_ss_raw(tbase + ACC_B2, al, hi, o_lo + ks * kstep, hi, id16, acc);
-              } else if (j == 2) {
-                mma_ss_raw(tbase + ACC_W1, al, hi, b_lo + ks * kstep, hi, id128, acc);
-                if (pb == 0) mma_ss_raw(tbase + ACC_B1, al, hi, o_lo + ks * kstep, hi, id16, acc);
-              } else if (j == 3) {
-                mma_ss_raw(tbase + ACC_W0F, al, hi, f_lo + ks * kstep, hi, id32, acc);
-              } else {
-                mma_ss_raw(tbase + ACC_W4, al, hi, x_lo + ks * kstep, hi, id16, acc);
-              }
-            }
+            for (uint32_t ks = 0; ks < 8; ++ks)
+              mma_ss_raw(tbase + acc_col, a_lo + ks * kstep, hi, b_lo + ks * kstep, hi, idesc, started | (ks > 0 ? 1u : 0u));
             mma_commit_raw(&bars[WB_EMPTY + st]);
           }
           __syncwarp();
+          BH_TIMING_END(t_wi)
         }
-        if (ok) { if (elect_one()) mma_commit_raw(&bars[WB_FEMPTY + fs]); __syncwarp(); }
-        ++fcnt; later_tile = 1;
+        later_tile = 1;
       }
       if (elect_one()) mma_commit_raw(&bars[WB_DONE]);
       __syncwarp();
+#ifdef BH_TC_TIMING
+      if (lane == 0) {
+        long long t_wl = clock64() - t_w0;
+        BH_TIMING_STORE_B(status, 44, t_fu, FUSED ? 1 : 0)
+        BH_TIMING_STORE_B(status, 46, t_wi, FUSED ? 1 : 0) BH_TIMING_STORE_B(status, 48, t_wl, FUSED ? 1 : 0)
+      }
+#endif
     }
     __syncwarp();
   } else if (warp < 4 && has_work) {
@@ -523,11 +564,11 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
           int dst = -1;
           if (c < ACC_W3F) dst = OFF_W3 + (int)c * 128 + n;
           else if (c < ACC_W2) { int kf = (int)(c - ACC_W3F); dst = kf < BH_NF ? OFF_W3 + (128 + kf) * 128 + n : (kf == TC_ONES_COL ? OFF_B3 + n : -1); }
-          else if (c < ACC_W1) dst = OFF_W2 + (int)(c - ACC_W2) * 128 + n;
-          else if (c < ACC_W0F) dst = OFF_W1 + (int)(c - ACC_W1) * 128 + n;
-          else if (c < ACC_B2) { int kf = (int)(c - ACC_W0F); dst = kf < BH_NF ? OFF_W0 + kf * 128 + n : (kf == TC_ONES_COL ? OFF_B0 + n : -1); }
-          else if (c < ACC_B1) dst = (c - ACC_B2 == TC_ONES_COL - 16) ? OFF_B2 + n : -1;
-          else if (c < ACC_W4) dst = (c - ACC_B1 == TC_ONES_COL - 16) ? OFF_B1 + n : -1;
+          else if (c < ACC_B2) dst = OFF_W2 + (int)(c - ACC_W2) * 128 + n;
+          else if (c < ACC_W1) dst = (c - ACC_B2 == TC_ONES_COL - 16) ? OFF_B2 + n : -1;
+          else if (c < ACC_B1) dst = OFF_W1 + (int)(c - ACC_W1) * 128 + n;
+          else if (c < ACC_W0F) dst = (c - ACC_B1 == TC_ONES_COL - 16) ? OFF_B1 + n : -1;
+          else if (c < ACC_W4) { int kf = (int)(c - ACC_W0F); dst = kf < BH_NF ? OFF_W0 + kf * 128 + n : (kf == TC_ONES_COL ? OFF_B0 + n : -1); }
           else dst = (c <= ACC_W4 + 1) ? OFF_W4 + n : -1;       // cols 0,1: h3^T dout_hi + h3^T dout_lo
           if (dst >= 0 && val != 0.f) atomicAdd(d_params + dst, val);
         }

@@ -28,7 +28,11 @@ __host__ __device__ constexpr uint32_t tc_stage_off(int l) {                    
 // (col 0 = hi, col 1 = lo bf16 part of d loss / d o).
 #define TC_ONES_COL 21
 #define TC_AIMG_BYTES 4096u              // 128 x 16 bf16
-__host__ __device__ inline size_t tc_acts_bytes_per_frame(int n_pad, int PL) { return (size_t)n_pad * (size_t)PL * (1024u + 64u); }
+//   relu masks  [tile][l=0..3][column half][row][2 words] at PL*n_pad*1088: one bit per activation (h > 0), 64 B per
+//               sample; all the dgrad chain needs of the activations (tc_mask_bits / tc_mask_expand below)
+__host__ __device__ inline size_t tc_acts_bytes_per_frame(int n_pad, int PL) { return (size_t)n_pad * ((size_t)PL * (1024u + 64u) + 64u); }
+__host__ __device__ inline size_t tc_mask_off(int n_pad, int PL) { return (size_t)n_pad * (size_t)PL * (1024u + 64u); }
+#define TC_MASK_TILE_BYTES 8192u         // 4 layers x 2 halves x 128 rows x 8 B
 __host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { return (size_t)n_pad * ((size_t)PL * 1024u + 32u); }
 #define TC_W_BYTES 229376u               // 16K + 64K + 64K + 80K
 #define TC_STAGE_MAX 81920u
@@ -46,6 +50,24 @@ __host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { 
 #define TC_C_B(l) ((l) * 128)
 #define TC_C_W4 512
 #define TC_C_B4 640
+
+// Optional cycle accounting (-DBH_TC_TIMING): block 0 writes, per role, the cycles spent waiting vs working into
+// the workspace status words [8..20) (two int32 per counter).  Compiled out by default.
+#ifdef BH_TC_TIMING
+#define BH_TIMING_DECL(v) long long v = 0; long long _t0_##v = 0; (void)_t0_##v;
+#define BH_TIMING_BEGIN _bh_t0 = clock64();
+#define BH_TIMING_END(v) v += clock64() - _bh_t0;
+#define BH_TIMING_T0 long long _bh_t0 = 0;
+#define BH_TIMING_STORE_B(st, i, v, blk) if (blockIdx.x == (blk)) { (st)[i] = (int)(v & 0xffffffffll); (st)[(i) + 1] = (int)(v >> 32); }
+#define BH_TIMING_STORE(st, i, v) BH_TIMING_STORE_B(st, i, v, 0)
+#else
+#define BH_TIMING_T0
+#define BH_TIMING_DECL(v)
+#define BH_TIMING_BEGIN
+#define BH_TIMING_END(v)
+#define BH_TIMING_STORE(st, i, v)
+#define BH_TIMING_STORE_B(st, i, v, blk)
+#endif
 
 namespace tc {
 using namespace umma;
@@ -80,6 +102,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // pull `bytes` (multiple of 16) of global memory into L2 ahead of their use; one instruction, no destination
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
+// ---- ReLU bit masks ----
+// One 32-bit word covers 32 consecutive columns = 16 packed bf16 pairs.  Pair j (columns 2j, 2j+1) keeps its two bits
+// at positions p and p + 16 with p = 8*(j&1) + 7 - (j>>1): after a left shift by (j>>1) they are the sign bits of
+// bytes (j&1) and (j&1)+2, and ONE prmt with sign replication expands them to the 0xffff / 0x0000 halves that mask
+// a packed pair -- the same two instructions per pair as a compare against the saved activation, without loading it.
+__device__ __forceinline__ constexpr uint32_t tc_mask_pair_bits(int j) {
+  return (1u << (8 * (j & 1) + 7 - (j >> 1))) | (1u << (8 * (j & 1) + 7 - (j >> 1) + 16));
+}
+// bits of pair j from a packed bf16 pair of (relu'd) activations
+__device__ __forceinline__ uint32_t tc_mask_bits(uint32_t h2, int j) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&h2), __float2bfloat162_rn(0.f)) & tc_mask_pair_bits(j);
+}
+// 0xffff per half of pair j where the activation was positive
+__device__ __forceinline__ uint32_t tc_mask_expand(uint32_t word, int j) {
+  uint32_t r;
+  const uint32_t t = word << (j >> 1);
+  if (j & 1) asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(r) : "r"(t));
+  else asm("prmt.b32 %0, %1, 0, 0xAA88;" : "=r"(r) : "r"(t));
+  return r;
+}
+// this thread's two mask words of layer l (row = sample row of the tile, half = 64-column half)
+__device__ __forceinline__ size_t tc_mask_word_off(int tile, int l, int half, int row) {
+  return (size_t)tile * TC_MASK_TILE_BYTES + (size_t)((l * 2 + half) * 128 + row) * 8u;
 }
 
 __device__ __forceinline__ uint32_t sample_img_off(int row, int colgroup) {   // 16-byte chunk of 8 columns

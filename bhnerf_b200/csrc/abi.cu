@@ -82,6 +82,15 @@ extern "C" int64_t bhnerf_launch_count(void) {
   return (int64_t)t;
 }
 
+extern "C" int bhnerf_workspace_status(const void* workspace, int32_t* flags_host, void* stream) {
+  BH_REQUIRE(workspace && flags_host, "workspace_status: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_CHECK_CUDA(cudaMemcpyAsync(flags_host, workspace, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  BH_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int i = 5; i < 8; ++i) flags_host[i] = 0;        // words past the flags hold optional cycle counters
+  return 0;
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static FrameConsts frame_consts(const bhnerf_scene_t* sc) {
   FrameConsts fc; fc.t_start_obs = sc->t_start_obs; fc.GM_c3 = sc->GM_c3; fc.t_injection = sc->t_injection;

@@ -47,13 +47,54 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ params, uint
     }
     if (idx == 0) c[TC_C_B4] = params[OFF_B4];
     if (idx < 64) ((int*)(ws + TC_WS_STATUS))[idx] = 0;
+    if (blockIdx.x == 0) {
+      // Can a hidden activation leave the fp16 operand range?  With |coords/scale| <= 4 and |sin| <= 1:
+      //   B_0 = max_n sum_k f_k |W0[k][n]| + |b0[n]| (f_k = 4 for k < 3, else 1),
+      //   B_l = max_n B_{l-1} sum_k |W_l[k][n]| + |b_l[n]|   (l = 1, 2)
+      // bound h0, h1, h2 -- the operands the forward rounds to fp16.  If a bound exceeds 6e4 (or is NaN) the epilogue
+      // tracks max|h| per sample and flags status word 3; otherwise that check costs nothing.
+      __shared__ float red[128];
+      float B = 1.f, need = 0.f;
+      const int woffs[3] = {OFF_W0, OFF_W1, OFF_W2}, boffs[3] = {OFF_B0, OFF_B1, OFF_B2}, kr[3] = {21, 128, 128};
+      for (int l = 0; l < 3; ++l) {
+        if (threadIdx.x < 128) {
+          float sum = 0.f;
+          for (int k = 0; k < kr[l]; ++k) sum += fabsf(params[woffs[l] + k * 128 + threadIdx.x]) * ((l == 0 && k < 3) ? 4.f : 1.f);
+          red[threadIdx.x] = sum * B + fabsf(params[boffs[l] + threadIdx.x]);
+        }
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) {
+          if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]) + 0.f * (red[threadIdx.x] + red[threadIdx.x + o]);
+          __syncthreads();
+        }
+        B = red[0];
+        if (!(B <= 6.0e4f)) need = 1.f;
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) c[TC_C_RANGE] = need;
+    }
     return;
   }
   if (idx >= K * 128) return;
   int k = idx >> 7, n = idx & 127;
   const int woff[4] = {OFF_W0, OFF_W1, OFF_W2, OFF_W3};
+  const int boff[4] = {OFF_B0, OFF_B1, OFF_B2, OFF_B3};
   const int krows[4] = {21, 128, 128, 149};
   float w = (k < krows[l]) ? params[woff[l] + k * 128 + n] : 0.f;
+  // The bias rides on the MMA: feature columns TC_ONES_COL and TC_ONES_COL+1 are the constant 1, and the weight
+  // rows they meet hold fp16(b) and b - fp16(b) (both exact in the hi plane).  Layers 0 and 3 contract over the
+  // feature image anyway (rows 21,22 / 149,150); layers 1 and 2 get a 16-row bias image of their own (below).
+  const float bias = params[boff[l] + n];
+  const float bias_hi = __half2float(__float2half_rn(bias));
+  if (l == 0 || l == 3) {
+    if (k == krows[l]) w = bias_hi;
+    if (k == krows[l] + 1) w = bias - bias_hi;
+  } else if (k < 16) {       // bias image [16 rows = feature cols 16..31][128], hi plane only (lo plane stays zero)
+    const int kf = 16 + k;
+    const float wb = kf == TC_ONES_COL ? bias_hi : (kf == TC_ONES_COL + 1 ? bias - bias_hi : 0.f);
+    uint8_t* bimg = ws + TC_WS_W + TC_W_BYTES + (uint32_t)(l - 1) * TC_BIMG_BYTES;
+    *reinterpret_cast<__half*>(bimg + img_off(k, n, TC_IMG_RS, 2u * 128u)) = __float2half_rn(wb);
+  }
   uint32_t off = img_off(k, n, TC_IMG_RS, (uint32_t)(K / 8) * 128u);
   {   // forward: fp16 hi/lo planes
     __half hi = __float2half_rn(w);
@@ -103,6 +144,9 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t tmem_a, ui
       }
     }
   }
+  if (L == 1 || L == 2)      // + [feature cols 16..31] x bias image: adds b_hi + b_lo through the two constant-1 columns
+    mma_ss_raw(tmem_d, a_lo[0] + ((2u * TC_SIMG_CS) >> 4), a_hi, desc_lo(w_smem + 2u * plane, TC_IMG_RS), desc_hi(2u * 128u),
+               idesc, 1u);
 }
 
 // ---- branch-free sine of the reference's reduced argument r in [0, 2*100pi) (safe_sin, network.py:16) ----
@@ -121,10 +165,24 @@ __device__ __forceinline__ float sin_reduced(float r) {
   const float val = (q & 1) ? cs : sn;
   return (q & 2) ? -val : val;
 }
+// Default: two-constant Cody-Waite reduction by 2*pi (j <= 100, j*6.28125 exact) + MUFU.SIN, abs error 2^-21.4 on
+// [-pi, pi] -- 7 instructions instead of ~20 for the polynomial pair above (-DBH_EXP_POLYSIN selects that one); the
+// epilogue warps are issue-bound, so this is 7 % of the forward (2.91 vs 3.13 ms, cfg2 x 25 frames) at unchanged
+// image / gradient error against the oracle (1.9e-6 / 1.2e-4).
+__device__ __forceinline__ float sin_reduced_mufu(float r) {
+  const float j = rintf(r * 0.15915494309189535f);
+  float x = fmaf(-j, 6.28125f, r);
+  x = fmaf(-j, 1.9353071795864769e-3f, x);
+  return __sinf(x);
+}
 __device__ __forceinline__ float safe_sin_fast(float a) {      // same float32 ARGUMENT arithmetic as bh_safe_sin
   float r = (fabsf(a) < BH_100PI_F) ? a : fmodf(a, BH_100PI_F);
   if (r < 0.0f) r = __fadd_rn(r, BH_100PI_F);
+#ifdef BH_EXP_POLYSIN
   return sin_reduced(r);
+#else
+  return sin_reduced_mufu(r);
+#endif
 }
 
 // warped + scaled coordinates of one sample (bh_features without the encodings)
@@ -162,11 +220,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn_relu(float lo, float hi) {
 constexpr uint32_t SM_PART = SM_BARS + 128;                        // [slot][row] partial of the last layer
 constexpr uint32_t SM_TOTAL2 = SM_PART + 2 * 128 * 4;
 
-template <int NPASS, int SAVE>      // SAVE = bf16 planes of every activation kept for the backward (0, 1, 2)
-__global__ void __launch_bounds__(kThreads, 1)
-tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, const float* __restrict__ t_frames,
-              int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts, int* __restrict__ status) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+// SAVE = bf16 planes of every activation kept for the backward (0, 1, 2).  RANGE = track max|h| per sample: compiled
+// as a second body of the same kernel and entered only when the weight bound of tc_prepare_weights_kernel cannot
+// rule out an fp16 operand overflow (the tracking costs ~10 % of the forward, so the usual path does not carry it).
+template <int NPASS, int SAVE, bool RANGE>
+__device__ __forceinline__ void
+tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uint8_t* __restrict__ ws,
+            const float* __restrict__ t_frames, int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts,
+            int* __restrict__ status) {
   uint8_t* wst = smem + SM_WSTAGE;
   uint8_t* featimg = smem + SM_FEAT;
   float* cst = (float*)(smem + SM_CONST);
@@ -208,8 +269,12 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
           uint32_t st = wcnt & 1u;
           ok = wait(&bars[BAR_WEMPTY + st], ((wcnt >> 1) & 1u) ^ 1u, ab);
           if (!ok) break;
-          mbar_expect_tx(&bars[BAR_WFULL + st], tc_stage_bytes(l));
+          const bool bimg = (l == 1 || l == 2);
+          mbar_expect_tx(&bars[BAR_WFULL + st], tc_stage_bytes(l) + (bimg ? TC_BIMG_BYTES : 0u));
           bulk_g2s(wst + st * TC_STAGE_MAX, ws + TC_WS_W + tc_stage_off(l), tc_stage_bytes(l), &bars[BAR_WFULL + st]);
+          if (bimg)
+            bulk_g2s(wst + st * TC_STAGE_MAX + tc_stage_bytes(l), ws + TC_WS_W + TC_W_BYTES + (uint32_t)(l - 1) * TC_BIMG_BYTES,
+                     TC_BIMG_BYTES, &bars[BAR_WFULL + st]);
         }
         if (!ok) break;
       }
@@ -294,6 +359,10 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
       BH_TIMING_BEGIN
       float u[3];
       const bool valid = warp_coords(in_x, in_y, in_z, in_om, in_tg, bh_frame_time(in_tf, fc), fc, u);
+      // the activation bound of tc_prepare_weights_kernel assumes |feature| <= 1; outside it, track the range per sample
+      // the weight bound assumes |coords/scale| <= 4 (the reference uses scale = rmax, i.e. <= 1): outside it the range
+      // cannot be vouched for without tracking
+      if (!RANGE && fmaxf(fmaxf(fabsf(u[0]), fabsf(u[1])), fabsf(u[2])) > 4.f) abort_s[1] = 1;
       const int ray = in_ray;
       load_inputs(r + 1);
       uint8_t* feat_save = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) +
@@ -314,8 +383,8 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
             for (int c = 0; c < 3; ++c)
               f[4 + 3 * ii + c] = safe_sin_fast(__fadd_rn(u[c] * (float)(1 << ii), BH_HALFPI_F));     // cols 12..20
           f[0] = f[1] = f[2] = f[3] = 0.f;
-          f[13] = SAVE ? 1.f : 0.f;      // col 21 = 1: zero weight rows there; wgrad reads bias gradients off it
-          f[14] = f[15] = 0.f;
+          f[13] = f[14] = 1.f;           // cols 21, 22 = 1: the weight rows they meet carry the bias (hi, lo parts)
+          f[15] = 0.f;
         }
         // half 0: chunk 0 (cols 0..7) + first 8 bytes of chunk 1 (cols 8..11)
         // half 1: last 8 bytes of chunk 1 (cols 12..15) + chunk 2 (cols 16..23) [+ zero chunk 3 of the saved copy]
@@ -338,7 +407,8 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
             *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + o2) = lB;
           }
         }
-        if (SAVE) {                                     // the backward's operands are bf16 (range of the cotangents)
+        if (SAVE) {                                     // the backward's operands are bf16 (range of the cotangents);
+          if (half == 1) f[14] = 0.f;                   // its copy keeps ONE constant-1 column: wgrad reads d bias off it
           split8(f, hA, lA);
           split8(f + 8, hB, lB);
           const size_t lo_off = (size_t)v.n_pad * 64u;
@@ -366,7 +436,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
       if (lane == 0) mbar_arrive(&bars[BAR_AREADY + slot]);
       BH_TIMING_END(t_ft)
       uint8_t* act_tile = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + (size_t)tile * TC_SIMG_BYTES : nullptr;
-      float o = 0.f;
+      float o = 0.f, xmax = 0.f;                        // xmax: largest activation written as an fp16 operand
       for (int l = 0; l < 4; ++l) {
         BH_TIMING_BEGIN
         ok = wait(&bars[BAR_DREADY + slot], d_phase, ab);
@@ -385,16 +455,24 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c0 = half * 64 + cc * 32;
-          const float* bias = cst + TC_C_B(l) + c0;
-          float x[32];
+          float x[32];                                  // pre-activation (the bias came through the MMA)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(raw[cc][j]) + bias[j];        // pre-activation
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(raw[cc][j]);
           uint32_t hi[16], lo[16];
           if (l < 3) {                                  // next layer's A operand: fp16 hi/lo planes in TMEM
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               hi[j] = pack_f16x2_rz_relu(x[2 * j], x[2 * j + 1]);
-              if (NPASS > 1) lo[j] = pack_f16x2_rn_relu(x[2 * j] - f16_lo(hi[j]), x[2 * j + 1] - f16_hi(hi[j]));
+              // lo = x - hi: hi is x rounded toward zero to 11 significant bits, i.e. x with the low 13 mantissa bits
+              // cleared (for x <= 0 the relu-conversion gives 0 either way; below the fp16 normal range the two differ
+              // by < 2^-24 absolute).  A mask instead of two f16->f32 conversions: the conversion pipe is what binds
+              // this epilogue (fwd 3.09 -> 2.78 ms on cfg2 x 25 frames).
+              if (NPASS > 1) lo[j] = pack_f16x2_rn_relu(x[2 * j] - __uint_as_float(__float_as_uint(x[2 * j]) & 0xFFFFE000u),
+                                                        x[2 * j + 1] - __uint_as_float(__float_as_uint(x[2 * j + 1]) & 0xFFFFE000u));
+            }
+            if (RANGE) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xmax = fmaxf(fmaxf(x[2 * j], x[2 * j + 1]), xmax);
             }
             tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), hi);
             if (NPASS > 1) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), lo);
@@ -433,6 +511,7 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
         BH_TIMING_END(t_ep)
       }
       if (!ok) break;
+      if (RANGE && xmax > 65504.f) abort_s[1] = 1;      // fp16 operand range exceeded (hi saturates): flag, do not hide
       // last layer: the two halves of a row combine their partial dot products through shared memory
       if (half == 1) {
         part[slot * 128 + row] = o;
@@ -453,6 +532,20 @@ tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, cons
   if (tid == 0 && *abort_s) atomicExch(status, 1);
   if (tid == 0 && abort_s[1]) atomicExch(status + 3, 1);
 }
+
+template <int NPASS, int SAVE>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, const float* __restrict__ t_frames,
+              int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+#ifndef BH_EXP_NORANGE
+  if (((const float*)(ws + TC_WS_CONST))[TC_C_RANGE] != 0.f)
+    tc_fwd_body<NPASS, SAVE, true>(smem, v, fc, ws, t_frames, Bt, e_out, acts, status);
+  else
+#endif
+    tc_fwd_body<NPASS, SAVE, false>(smem, v, fc, ws, t_frames, Bt, e_out, acts, status);
+}
+
 
 int g_num_sms = 0;
 int num_sms() {

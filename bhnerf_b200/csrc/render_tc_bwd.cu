@@ -30,6 +30,13 @@ namespace {
 constexpr int kDThreads = 576;           // 16 epilogue warps + MMA issuer + weight loader
 constexpr int kDMmaWarp = 16;
 constexpr uint32_t DW_BYTES = TC_W_BYTES - 16384u;                 // stages of layers 1..3, contiguous in ws
+// "unit cotangent" plan (U16, one-plane steps): the chain runs on u_l = delta_l / (d loss/d o), which is a product of
+// weights and ReLU masks only -- bounded like the weights, so fp16 (11 significand bits) holds it and the forward's
+// fp16 hi weight planes serve as B.  ONE product per layer instead of two (d_hi*W_hi + d_hi*W_lo with bf16), half the
+// shared memory (104 KB), and the systematic error is the fp16 rounding of W (2^-12) instead of bf16's 2^-9.
+// The epilogue multiplies by d loss/d o in fp32 when it writes the bf16 delta images for the wgrad CTA.
+constexpr uint32_t DW_BYTES_U16 = 32768u + 32768u + 40960u;        // fp16 hi planes of layers 1..3
+__host__ __device__ constexpr uint32_t u16_w_off(int l) { return l == 1 ? 0u : (l == 2 ? 32768u : 65536u); }
 constexpr uint32_t D_SM_W = 0;
 constexpr uint32_t D_SM_W4 = DW_BYTES;                             // 128 floats
 constexpr uint32_t D_SM_BARS = D_SM_W4 + 512;
@@ -73,7 +80,14 @@ tc_dout_kernel(PackedView v, const float* __restrict__ d_images, const float* e,
   }
 }
 
-template <int PL, bool FUSED>
+// masked fp16 pair of the unit cotangents (TMEM operand of the next layer) and masked bf16 pair of the true
+// cotangents u * dout (delta image for the wgrad)
+__device__ __forceinline__ void unit_pack(uint32_t m, float a, float b, float dout, uint32_t& u16, uint32_t& d16) {
+  u16 = pack_f16x2(a, b) & m;
+  d16 = pack_bf16x2(a * dout, b * dout) & m;
+}
+
+template <int PL, bool FUSED, bool U16>
 __device__ __forceinline__ void
 dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, const PackedView& v,
            const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
@@ -106,17 +120,23 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
   const uint32_t tbase = *tmem_base_s;
 
   if (warp == kDMmaWarp + 1) {
-    if (lane == 0) {      // resident weights: layers 1..3 [hi|lo] images, one shot
-      mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
-      const uint8_t* src = ws + TC_WS_WB + 16384u;
-      bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
-      bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
-      bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
+    if (lane == 0) {      // resident weights, one shot
+      if (U16) {          // fp16 hi planes of the forward's images, layers 1..3
+        mbar_expect_tx(&bars[DB_WFULL], DW_BYTES_U16);
+        for (int l = 1; l <= 3; ++l)
+          bulk_g2s(wsm + u16_w_off(l), ws + TC_WS_W + tc_stage_off(l), tc_plane_bytes(l), &bars[DB_WFULL]);
+      } else {            // bf16 [hi|lo] images, layers 1..3
+        mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
+        const uint8_t* src = ws + TC_WS_WB + 16384u;
+        bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
+        bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
+        bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
+      }
     }
     __syncwarp();
   } else if (warp == kDMmaWarp) {
     {   // whole warp runs the loop; elect.sync inside the issue wrappers picks the issuing lane
-      const uint32_t idesc = make_idesc(128, 128, 0, 0);      // A from TMEM, B K-major
+      const uint32_t idesc = U16 ? make_idesc_f16(128, 128, 0, 0) : make_idesc(128, 128, 0, 0);   // A from TMEM, B K-major
       uint32_t a_phase[2] = {0u, 0u};
       BH_TIMING_T0 BH_TIMING_DECL(t_wa) BH_TIMING_DECL(t_is)
       bool ok = wait(&bars[DB_WFULL], 0, ab);
@@ -124,7 +144,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         int T0 = (r * ncta + cta) * 2;
         if (T0 >= NT) break;
         for (int l = 3; l >= 1 && ok; --l) {
-          const uint32_t wl = smem_u32(wsm) + tc_stage_off(l) - 16384u;
+          const uint32_t wl = smem_u32(wsm) + (U16 ? u16_w_off(l) : tc_stage_off(l) - 16384u);
           const uint32_t plane = tc_plane_bytes(l), cs = (tc_layer_K(l) / 8u) * 128u;
           for (int s = 0; s < 2; ++s) {
             if (T0 + s >= NT) continue;
@@ -142,7 +162,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
               const uint32_t b_hi = desc_hi(TC_IMG_RS), b_lo0 = desc_lo(wl, cs), b_lo1 = desc_lo(wl + plane, cs);
               const uint32_t kstep = (2u * cs) >> 4;
 #pragma unroll
-              for (int pp = 0; pp < (PL == 2 ? 3 : 2); ++pp)
+              for (int pp = 0; pp < (U16 ? 1 : (PL == 2 ? 3 : 2)); ++pp)
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                   mma_ts_raw(td, ta + (pp == 2 ? 64u : 0u) + (uint32_t)ks * 8u, (pp == 1 ? b_lo1 : b_lo0) + (uint32_t)ks * kstep,
@@ -244,6 +264,13 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
           const uint32_t mw = cc ? mk[3].y : mk[3].x;
           const float* w4 = w4s + (cg0 + 4 * cc + gq) * 8;
+          if (U16) {       // d = unit cotangent W4 .* mask (fp16, chain operand); dl = dout * W4 .* mask (bf16, delta image)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              unit_pack(tc_mask_expand(mw, 4 * gq + jj), w4[2 * jj], w4[2 * jj + 1], dout, d[4 * gq + jj], dl[4 * gq + jj]);
+            BH_DSTORE(del_tile + 3 * dls + off, make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]));
+            continue;
+          }
           delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
           delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
           delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
@@ -286,6 +313,14 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
             const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
             const uint32_t mw = cc ? mkl.y : mkl.x;
             const uint32_t* rr = raw[cc] + 8 * gq;
+            if (U16) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                unit_pack(tc_mask_expand(mw, 4 * gq + jj), __uint_as_float(rr[2 * jj]), __uint_as_float(rr[2 * jj + 1]), dout,
+                          d[4 * gq + jj], dl[4 * gq + jj]);
+              BH_DSTORE(d_img + off, make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]));
+              continue;
+            }
             delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), __uint_as_float(rr[0]), __uint_as_float(rr[1]), d[4 * gq + 0], dl[4 * gq + 0]);
             delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), __uint_as_float(rr[2]), __uint_as_float(rr[3]), d[4 * gq + 1], dl[4 * gq + 1]);
             delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), __uint_as_float(rr[4]), __uint_as_float(rr[5]), d[4 * gq + 2], dl[4 * gq + 2]);
@@ -330,13 +365,14 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
   if (tid == 0 && *abort_s) atomicExch(status + 1, 1);
 }
 
-template <int PL>
+template <int PL, bool U16>
 __global__ void __launch_bounds__(kDThreads, 1)
 tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
                 const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
                 float* __restrict__ d_params, int* __restrict__ status) {
+  static_assert(!(U16 && PL == 2), "the unit-cotangent plan is a one-plane plan");
   extern __shared__ __align__(1024) uint8_t smem[];
-  dgrad_role<PL, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, dout_all, Bt, acts,
+  dgrad_role<PL, false, U16>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, dout_all, Bt, acts,
                         deltas, d_params, status);
 }
 
@@ -410,7 +446,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
     for (int s = 0; s < kWStages; ++s) { mbar_init(&bars[WB_FULL + s], 1); mbar_init(&bars[WB_EMPTY + s], 1); }
     mbar_init(&bars[WB_DONE], 1);
     for (int s = 0; s < kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], 8);
-    *abort_s = 0;
+    abort_s[0] = 0; abort_s[1] = 0;
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(tmem_base_s, 512);
@@ -571,6 +607,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
           else if (c < ACC_W4) { int kf = (int)(c - ACC_W0F); dst = kf < BH_NF ? OFF_W0 + kf * 128 + n : (kf == TC_ONES_COL ? OFF_B0 + n : -1); }
           else dst = (c <= ACC_W4 + 1) ? OFF_W4 + n : -1;       // cols 0,1: h3^T dout_hi + h3^T dout_lo
           if (dst >= 0 && val != 0.f) atomicAdd(d_params + dst, val);
+          if (dst >= 0 && !(fabsf(val) <= 3.0e38f)) abort_s[1] = 1;     // cotangent overflow (fp16 unit chain): flag it
         }
       }
     }
@@ -580,6 +617,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
   if (FUSED) cluster_sync_all();
   if (warp == 4) tmem_dealloc(tbase, 512);
   if (tid == 0 && *abort_s) atomicExch(status + 2, 1);
+  if (tid == 0 && abort_s[1]) atomicExch(status + 4, 1);
 }
 
 template <int PL>
@@ -595,6 +633,7 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
 // =====================================================================================================
 constexpr uint32_t F_SM_TOTAL = D_SM_TOTAL > WCfg<1>::SM_TOTAL ? D_SM_TOTAL : WCfg<1>::SM_TOTAL;
 
+template <bool U16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
 tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
                     const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
@@ -606,7 +645,7 @@ tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* _
   link.ring = ring + (size_t)pair * kRingDepth * TSET_BYTES;
   if (rank == 0) {
     link.peer_bars = mapa_u32(smem_u32(smem + WCfg<1>::SM_BARS + WB_GFULL * 8), 1u);
-    dgrad_role<1, true>(smem, pair, npairs, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
+    dgrad_role<1, true, U16>(smem, pair, npairs, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
   } else {
     link.peer_bars = mapa_u32(smem_u32(smem + D_SM_BARS + DB_GFREE * 8), 0u);
     wgrad_role<1, true>(smem, pair, npairs, link, v.n_pad, Bt, acts, nullptr, d_params, status);
@@ -621,6 +660,16 @@ int num_sms_b() {
     if (g_num_sms_b <= 0) g_num_sms_b = 148;
   }
   return g_num_sms_b;
+}
+
+// BHNERF_TC_DGRAD=f16 selects the unit-cotangent fp16 chain.  Measured on B200 (profiles/r1_cycles_bwd_v5.log): it halves
+// the chain's MMA time but the chain is bound by its epilogue latency, not by the tensor pipe -- the extra pack per
+// element makes the backward 10 % SLOWER (3.42 vs 3.09 ms) and the gradient less exact (2.7e-4 vs 1.1e-4), so the
+// two-product bf16 chain stays the default.
+bool dgrad_u16_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("BHNERF_TC_DGRAD"); on = (e && e[0] == 'f') ? 1 : 0; }
+  return on == 1;
 }
 
 bool bwd_fused_enabled() {                 // BHNERF_TC_FUSED=0 selects the two-kernel backward (A/B measurements)
@@ -643,19 +692,21 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
   }
   if (PL == 1 && bwd_fused_enabled()) {
     BhProfScope ps(BH_CAT_BWD, 1, st);
-    BH_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SM_TOTAL));
+    auto kern = dgrad_u16_enabled() ? tc_bwd_fused_kernel<true> : tc_bwd_fused_kernel<false>;
+    BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SM_TOTAL));
     int npairs = (NT + 1) / 2; if (npairs > num_sms_b() / 2) npairs = num_sms_b() / 2;
-    tc_bwd_fused_kernel<<<2 * npairs, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt,
-                                                                 (const uint8_t*)acts, (uint8_t*)delta_ws, d_params, status);
+    kern<<<2 * npairs, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts,
+                                                    (uint8_t*)delta_ws, d_params, status);
     BH_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
   {
     BhProfScope ps(BH_CAT_BWD, 1, st);
-    BH_CHECK_CUDA(cudaFuncSetAttribute(tc_dgrad_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SM_TOTAL));
+    auto kern = (PL == 1 && dgrad_u16_enabled()) ? tc_dgrad_kernel<PL, PL == 1> : tc_dgrad_kernel<PL, false>;
+    BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SM_TOTAL));
     int grid = (NT + 1) / 2; if (grid > num_sms_b()) grid = num_sms_b();
-    tc_dgrad_kernel<PL><<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt,
-                                                             (const uint8_t*)acts, (uint8_t*)delta_ws, d_params, status);
+    kern<<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts, (uint8_t*)delta_ws,
+                                              d_params, status);
     BH_CHECK_CUDA(cudaGetLastError());
   }
   {

@@ -35,21 +35,23 @@ __host__ __device__ inline size_t tc_mask_off(int n_pad, int PL) { return (size_
 #define TC_MASK_TILE_BYTES 8192u         // 4 layers x 2 halves x 128 rows x 8 B
 __host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { return (size_t)n_pad * ((size_t)PL * 1024u + 32u); }
 #define TC_W_BYTES 229376u               // 16K + 64K + 64K + 80K
+#define TC_BIMG_BYTES 4096u              // forward only: bias image of layer 1 / 2 (16 x 128 fp16) at TC_WS_W + TC_W_BYTES
 #define TC_STAGE_MAX 81920u
 
 // ---- global workspace (bh_tc_ws_bytes) -------------------------------------------------------
 //   [0,256)        int32 status words (0 = ok)
 //   [256,4096)     fp32 constants: b0,b1,b2,b3 (4x128) | W4 (128) | b4 (1)
-//   [4096, +224K)  fp16 weight images of the forward, per layer [hi plane | lo plane]
+//   [4096, +224K)  fp16 weight images of the forward, per layer [hi plane | lo plane]; then 2 x 4 KB bias images
 //   [262144,+224K) bf16 weight images of the dgrad chain (cotangents need the fp32 exponent range), same layout
 #define TC_WS_STATUS 0u
 #define TC_WS_CONST 256u
 #define TC_WS_W 4096u
 #define TC_WS_WB 262144u
-#define TC_CONST_FLOATS 768              // 641 used
+#define TC_CONST_FLOATS 768              // 642 used
 #define TC_C_B(l) ((l) * 128)
 #define TC_C_W4 512
 #define TC_C_B4 640
+#define TC_C_RANGE 641                   // != 0: the weights allow |h| > 65504, the forward epilogue tracks the range
 
 // Optional cycle accounting (-DBH_TC_TIMING): block 0 writes, per role, the cycles spent waiting vs working into
 // the workspace status words [8..20) (two int32 per counter).  Compiled out by default.

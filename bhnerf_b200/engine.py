@@ -57,6 +57,30 @@ def workspace(nbytes, device):
     return ws
 
 
+STATUS_FLAGS = ('forward pipeline aborted', 'dgrad chain aborted', 'wgrad aborted',
+                'forward activation exceeded the fp16 operand range (|h| > 65504): images invalid',
+                'backward produced a non-finite parameter gradient')
+
+
+def workspace_status(device=None, impl=None):
+    """Health flags of the last tcgen05 step on `device` (C ABI: bhnerf_workspace_status).  Synchronises the
+    stream: call it off the hot path (Optimizer.run polls it when it logs).  Raises BhnerfError if a flag is set."""
+    if resolve_impl(impl) != IMPL_TC:
+        return [0] * 8
+    device = torch.device(device if device is not None else 'cuda')
+    ws = _workspaces.get(device.index if device.index is not None else torch.cuda.current_device())
+    if ws is None:
+        return [0] * 8
+    flags = (C.c_int32 * 8)()
+    with torch.cuda.device(device):
+        check(_lib.load().bhnerf_workspace_status(_ptr(ws), flags, _stream()))
+    flags = list(flags)
+    bad = [STATUS_FLAGS[i] for i in range(len(STATUS_FLAGS)) if flags[i]]
+    if bad:
+        raise _lib.BhnerfError('bhnerf_b200 tcgen05 step failed: ' + '; '.join(bad))
+    return flags
+
+
 class PackedScene:
     """Prepacked, frame-independent scene: the non-optimised arguments of network.raytracing_args
     (bhnerf/network.py:850-894) + the NeRF_Predictor domain constants (bhnerf/network.py:147-157)."""

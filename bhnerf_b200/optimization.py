@@ -11,7 +11,7 @@ import pickle
 import numpy as np
 import torch
 
-from . import network, utils
+from . import engine, network, utils
 
 
 def _world():
@@ -245,6 +245,7 @@ class Optimizer(object):
 
     def save_checkpoint(self):
         if (self.checkpoint_dir != '') and ((self.step % self.save_period == 0) or (self.step == self.final_step)):
+            engine.workspace_status()       # never checkpoint a state an overflowed tcgen05 step produced (raises)
             if _world()[0] == 0:
                 save_checkpoint(self.checkpoint_dir, self.state, int(self.step), keep=self.keep)
 
@@ -262,6 +263,7 @@ class Optimizer(object):
                 self.save_checkpoint()
         except KeyboardInterrupt:
             return
+        engine.workspace_status()           # health flags of the last step (one sync, off the hot loop)
 
     @property
     def params(self):

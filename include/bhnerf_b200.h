@@ -159,6 +159,14 @@ int64_t bhnerf_launch_count(void);
 int bhnerf_profile_begin(void);
 int bhnerf_profile_end(double* ms_host, int64_t* scopes_host, int64_t* launches_host);
 
+/* ---- health flags of the last tcgen05 step that used `workspace` (the first bytes of every TC workspace;
+ * reset by the next step).  Synchronises `stream`.  flags_host[8]:
+ *   [0] forward pipeline aborted (a bounded mbarrier wait expired)   [1] dgrad chain aborted   [2] wgrad aborted
+ *   [3] forward: |activation| exceeded the fp16 operand range (65504) -> images invalid
+ *   [4] backward: non-finite parameter gradient (cotangent overflow)  [5..7] reserved (0)
+ * The reference has no counterpart (XLA fp32 cannot overflow here); callers poll this off the hot path.        */
+int bhnerf_workspace_status(const void* workspace, int32_t* flags_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

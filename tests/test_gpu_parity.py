@@ -294,3 +294,22 @@ def test_simt_and_tc_agree_at_config_shape():
     assert (it_ - is_).abs().max() / is_.abs().max() < IMG_TOL
     assert (gt - gs).abs().max() / gs.abs().max() < GRAD_TOL
     assert abs(lt.item() - ls.item()) / ls.item() < IMG_TOL
+
+
+def test_fp16_operand_overflow_is_flagged_not_hidden():
+    """The tcgen05 forward rounds hidden activations to fp16 operands.  Weights that push |h| past 65504 must raise
+    through bhnerf_workspace_status (status word 3), and healthy weights must leave every flag clear."""
+    from bhnerf_b200 import _lib, engine, testing
+    scene, d = testing.load_golden_scene('case_image_full')
+    tf = torch.as_tensor(d['t_frames'].astype(np.float32)).cuda()
+    good = torch.as_tensor(d['params_flat']).cuda()
+    engine.render_fwd(scene, good, tf, 'tc')
+    assert engine.workspace_status(impl='tc')[:5] == [0, 0, 0, 0, 0]
+    bad = good.clone()
+    bad[: 21 * 128 + 128] *= 3.0e4            # W0, b0: h0 ~ 3e4 x O(1..10)
+    bad[21 * 128 + 128: 21 * 128 + 128 + 128 * 128] *= 30.0
+    engine.render_fwd(scene, bad, tf, 'tc')
+    with pytest.raises(_lib.BhnerfError, match='fp16 operand range'):
+        engine.workspace_status(impl='tc')
+    engine.render_fwd(scene, good, tf, 'tc')  # flags are per step
+    assert engine.workspace_status(impl='tc')[3] == 0

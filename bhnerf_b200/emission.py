@@ -47,3 +47,69 @@ def fill_unsupervised_emission(emission, coords, rmin=0, rmax=np.inf, z_width=2.
                                                 float(rmin), float(min(rmax, 3.0e38)), float(min(z_width, 3.0e38)),
                                                 float(fill_value), engine._stream()))
     return e
+
+
+def _geo(geos, k):
+    return np.asarray(geos[k] if hasattr(geos, '__getitem__') and not hasattr(geos, k) else getattr(geos, k))
+
+
+def _grid_fov(emission_0, fov):
+    """Extent of the voxel grid per axis.  The reference reads it off the xarray coordinates
+    (emission[dim].max() - emission[dim].min(), bhnerf/emission.py:229); plain arrays need ``fov``."""
+    if fov is not None:
+        return [float(f) for f in np.broadcast_to(np.asarray(fov, dtype=np.float64), (3,))]
+    if hasattr(emission_0, 'dims'):
+        dims = list(emission_0.dims)[-3:]
+        return [float(np.asarray(emission_0[d]).max() - np.asarray(emission_0[d]).min()) for d in dims]
+    raise AttributeError('emission_0 carries no coordinates: pass fov=(fx, fy, fz) (extent of the grid in M)')
+
+
+def image_plane_dynamics(emission_0, geos, Omega, t_frames, t_injection, J=1.0, t_start_obs=None, slow_light=True,
+                         doppler=True, rot_axis=[0, 0, 1], M=constants.sgra_mass, fov=None, t_units=None):
+    """bhnerf/emission.py:234-303 on the GPU (csrc/grid.cu, mode 0): velocity warp -> trilinear lookup of the
+    voxel grid (scipy map_coordinates order=1, cval=0) -> J broadcast -> ray integral.  Returns a device tensor
+    (nt, [S,] A, B); an emission movie (ndim 4) gives (T, nt, [S,] A, B) as in the reference.
+
+    ``geos``: mapping / namespace with x, y, z, t, dtau, Sigma of shape (A, B, G) and, for doppler=True, either
+    ``g`` or the fields kgeo.doppler_factor needs.  ``fov`` / ``t_units`` are extensions for inputs without
+    xarray coordinates / astropy units (plain numbers are taken in units of M, as the reference does)."""
+    from . import kgeo as _kgeo
+    if list(np.asarray(rot_axis, dtype=float)) != [0.0, 0.0, 1.0]:
+        raise NotImplementedError('Currently only equitorial plane rotation is supported')
+    if hasattr(t_start_obs, 'unit'):
+        t_units = t_start_obs.unit
+    elif t_start_obs is None and hasattr(t_frames, 'unit'):
+        t_units = t_frames.unit
+    GM_c3 = constants.GM_c3(M, t_units) if t_units is not None else 1.0
+    tf = np.atleast_1d(np.asarray(utils.time_value(t_frames, t_units or 'hr'), dtype=np.float64))
+    t0 = float(tf[0]) if t_start_obs is None else float(utils.time_value(t_start_obs, t_units or 'hr'))
+    x, y, z = [np.asarray(_geo(geos, k), dtype=np.float32) for k in ('x', 'y', 'z')]
+    t_geos = np.asarray(_geo(geos, 't'), dtype=np.float32) if slow_light else np.zeros_like(x)
+    if doppler:
+        try:
+            g = np.asarray(_geo(geos, 'g'), dtype=np.float32)
+        except (KeyError, AttributeError):
+            g = _kgeo.doppler_factor(geos, _kgeo.azimuthal_velocity_vector(geos, Omega))
+    else:
+        g = np.ones_like(x)
+    e0 = np.asarray(emission_0, dtype=np.float32)
+    if e0.ndim not in (3, 4):
+        raise AttributeError('emission_0 must be a 3D grid or a 4D movie of grids')
+    fx, fy, fz = _grid_fov(emission_0, fov)
+    # samples outside the grid's bounding sphere / slab give exactly 0: let the prepack drop them
+    eps = 1.0 + 1e-5
+    rmax = eps * 0.5 * float(np.sqrt(fx * fx + fy * fy + fz * fz))
+    scene = engine.PackedScene(np.stack([x, y, z]), Omega, J, g, _geo(geos, 'dtau'), _geo(geos, 'Sigma'), t_geos, t0,
+                               float(t_injection), 1.0, 0.0, rmax, eps * 0.5 * fz, GM_c3)
+    grids = e0[None] if e0.ndim == 3 else e0
+    outs = []
+    for gr in grids:
+        images, _ = engine.grid_render_fwd(scene, gr, (fx, fy, fz), tf.astype(np.float32), engine.GRID_MODE_DYNAMICS)
+        Bt = images.shape[0]
+        img = images.reshape((Bt,) + scene.image_shape) if not scene.polarized else \
+            images.reshape((Bt, scene.S) + scene.image_shape)
+        outs.append(img)
+    out = outs[0] if e0.ndim == 3 else torch.stack(outs)
+    if np.ndim(utils.time_value(t_frames, t_units or 'hr')) == 0:
+        out = out[0] if e0.ndim == 3 else out[:, 0]
+    return out

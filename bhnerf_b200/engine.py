@@ -269,6 +269,44 @@ def vis_bwd(A, dvis, P):
     return dI
 
 
+GRID_MODE_DYNAMICS, GRID_MODE_PREDICTOR = 0, 1
+
+
+def _fov3(fov):
+    f = np.broadcast_to(np.asarray(fov, dtype=np.float64), (3,))
+    return [float(f[0]), float(f[1]), float(f[2])]
+
+
+def grid_render_fwd(scene, grid, fov, t_frames, mode, want_e=False):
+    """images [Bt,S,P] (and per-sample emission [Bt,n_pad]) of the voxel-grid renderer.  C ABI: bhnerf_grid_render_fwd."""
+    lib = _lib.load(); dev = scene.device
+    grid = _dev_f32(grid, dev); t_frames = _dev_f32(t_frames, dev).reshape(-1)
+    assert grid.dim() == 3
+    Bt = t_frames.numel()
+    images = torch.empty((Bt, scene.S, scene.P), dtype=torch.float32, device=dev)
+    e = torch.zeros((Bt, scene.n_pad), dtype=torch.float32, device=dev) if want_e else None
+    fx, fy, fz = _fov3(fov)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_grid_render_fwd(scene.ref, _ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2], fx, fy, fz,
+                                         int(mode), _ptr(t_frames), Bt, _ptr(images), _ptr(e), _stream()))
+    return images, e
+
+
+def grid_render_bwd(scene, grid, fov, t_frames, d_images):
+    """d_grid (same shape as grid) of GRID_Predictor's render.  C ABI: bhnerf_grid_render_bwd."""
+    lib = _lib.load(); dev = scene.device
+    grid = _dev_f32(grid, dev); t_frames = _dev_f32(t_frames, dev).reshape(-1)
+    d_images = _dev_f32(d_images, dev)
+    Bt = t_frames.numel()
+    assert d_images.numel() == Bt * scene.S * scene.P
+    d_grid = torch.empty_like(grid)
+    fx, fy, fz = _fov3(fov)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_grid_render_bwd(scene.ref, _ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2], fx, fy, fz,
+                                         _ptr(t_frames), Bt, _ptr(d_images), _ptr(d_grid), _stream()))
+    return d_grid
+
+
 def train_step_image(scene, params, t_frames, target, sigma, offset, scale, kind, impl=None, max_workspace=None,
                      out=None):
     """Fused fwd -> ray integral -> loss -> bwd.  Returns (loss[1], images [Bt,S,P], grads [55169]).

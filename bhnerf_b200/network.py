@@ -58,7 +58,7 @@ class TrainState:
 
     @property
     def params(self):
-        return unflatten_params(self.flat)
+        return self.predictor._unflatten(self.flat)
 
     def apply_gradients(self, grads, grad_scale=1.0):
         """optax.adam + polynomial_schedule(lr_init, lr_final, 1, num_iters) (network.py:173-174,:621)."""
@@ -110,6 +110,16 @@ class NeRF_Predictor:
     def domain(self):
         return dict(scale=self.scale, rmin=self.rmin, rmax=self.rmax, z_width=self.z_width)
 
+    # ---- what the step functions need from a predictor: flat parameters <-> pytree, render forward / pull-back ----
+    _unflatten = staticmethod(lambda flat: unflatten_params(flat))
+    _flatten = staticmethod(lambda params: flatten_params(params))
+
+    def _render_fwd(self, scene, flat, tf, impl=None, save_acts=False):
+        return engine.render_fwd(scene, flat, tf, impl, save_acts=save_acts)
+
+    def _render_bwd(self, scene, flat, tf, d_images, e, acts, impl=None):
+        return engine.render_bwd(scene, flat, tf, d_images, e, acts, impl)
+
     def apply(self, variables, t_frames, t_units, coords, Omega, t_start_obs, t_geos, t_injection, impl=None):
         """NeRF_Predictor.__call__ (network.py:191-237): emission on the given points, shape (Bt, *coords.shape[1:])
         (no Bt axis for a scalar t_frames).  Runs the forward kernel with unit ray weights."""
@@ -154,6 +164,94 @@ class NeRF_Predictor:
             return cls(**yaml.safe_load(f))
 
 
+class GRID_Predictor:
+    """bhnerf/network.py:254-370: a learnable grid_res^3 voxel grid instead of the MLP.  Same warp, domain fill and
+    injection mask; lookup = jax.scipy.ndimage.map_coordinates(order=1, cval=0) at (coords+scale)/(2 scale)*(res-1),
+    emission = sigmoid(v - 10).  Kernels: csrc/grid.cu (bhnerf_grid_render_fwd / _bwd, mode 1)."""
+
+    def __init__(self, scale=1.0, rmin=0.0, rmax=np.inf, z_width=np.inf, grid_res=64):
+        self.scale, self.rmin, self.rmax, self.z_width = float(scale), float(rmin), float(rmax), float(z_width)
+        self.grid_res = int(grid_res)
+
+    def init_params(self, raytracing_args=None, seed=1):
+        """network.py:305: grid initialised to -10 (emission sigmoid(-20) ~ 2e-9)."""
+        return {'grid': np.full((self.grid_res,) * 3, -10.0, dtype=np.float32)}
+
+    def init_state(self, params, num_iters=5000, lr_init=1e-4, lr_final=1e-6, lr_inject=None, checkpoint_dir='',
+                   device=None):
+        """network.py:287-303 (optax.adam + polynomial_schedule on the grid)."""
+        if lr_inject:
+            raise NotImplementedError('lr_inject: the t_injection parameter is commented out in the reference '
+                                      '(bhnerf/network.py:355)')
+        device = torch.device(device if device is not None else 'cuda')
+        state = TrainState(self, self._flatten(params), num_iters, lr_init, lr_final, device)
+        if checkpoint_dir:
+            from .optimization import restore_checkpoint
+            restore_checkpoint(checkpoint_dir, state)
+        return state
+
+    def domain(self):
+        return dict(scale=self.scale, rmin=self.rmin, rmax=self.rmax, z_width=self.z_width)
+
+    def _unflatten(self, flat):
+        g = flat.detach().cpu().numpy() if isinstance(flat, torch.Tensor) else np.asarray(flat)
+        return {'grid': g.reshape((self.grid_res,) * 3).copy()}
+
+    def _flatten(self, params):
+        g = params['grid'] if isinstance(params, dict) else params
+        g = g.detach().cpu().numpy() if isinstance(g, torch.Tensor) else np.asarray(g, dtype=np.float32)
+        assert g.size == self.grid_res ** 3, 'grid must be grid_res^3'
+        return np.ascontiguousarray(g, dtype=np.float32).reshape(-1)
+
+    def _grid(self, flat, device):
+        t = flat if isinstance(flat, torch.Tensor) else torch.as_tensor(self._flatten(flat), device=device)
+        return t.to(device=device, dtype=torch.float32).reshape((self.grid_res,) * 3)
+
+    def _render_fwd(self, scene, flat, tf, impl=None, save_acts=False):
+        images, e = engine.grid_render_fwd(scene, self._grid(flat, scene.device), 2.0 * self.scale, tf,
+                                           engine.GRID_MODE_PREDICTOR, want_e=save_acts)
+        return images, e, None
+
+    def _render_bwd(self, scene, flat, tf, d_images, e=None, acts=None, impl=None):
+        return engine.grid_render_bwd(scene, self._grid(flat, scene.device), 2.0 * self.scale, tf, d_images).reshape(-1)
+
+    def apply(self, variables, t_frames, t_units, coords, Omega, t_start_obs, t_geos, t_injection, impl=None):
+        """GRID_Predictor.__call__ (network.py:306-357): emission on the given points, (Bt, *coords.shape[1:])."""
+        params = variables['params'] if 'params' in variables else variables
+        coords = np.asarray(coords, dtype=np.float32)
+        pts_shape = coords.shape[1:]
+        c2 = coords.reshape(3, -1, 1) if coords.ndim == 2 else coords.reshape(3, -1, coords.shape[-1])
+        P, G = c2.shape[1], c2.shape[2]
+        ones = np.ones((P, G), dtype=np.float32)
+        Om = np.broadcast_to(np.asarray(Omega, dtype=np.float32), pts_shape).reshape(P, G)
+        tg = np.broadcast_to(np.asarray(t_geos, dtype=np.float32), pts_shape).reshape(P, G)
+        GM_c3 = constants.GM_c3(t_units=t_units) if t_units is not None else 1.0
+        scene = engine.PackedScene(c2, Om, 1.0, ones, ones, ones, tg, utils.time_value(t_start_obs, t_units or 'hr'),
+                                   float(t_injection), self.scale, self.rmin, self.rmax, self.z_width, GM_c3)
+        tf = np.atleast_1d(utils.time_value(t_frames, t_units or 'hr')).astype(np.float32)
+        _, e, _ = self._render_fwd(scene, params if isinstance(params, torch.Tensor) else self._flatten(params), tf,
+                                   save_acts=True)
+        dense = torch.zeros((len(tf), P * G), dtype=torch.float32, device=scene.device)
+        if scene.n_active:
+            dense[:, scene.dense_index] = e[:, :scene.n_active]
+        dense = dense.cpu().numpy().reshape((len(tf),) + tuple(pts_shape))
+        return dense[0] if np.ndim(t_frames) == 0 else dense
+
+    def save_params(self, directory, filename='GRID_Predictor_params.yml'):
+        """network.py:359-366 (the reference's key list names NeRF fields; only the ones this class has are written)."""
+        import yaml
+        os.makedirs(directory, exist_ok=True)
+        with open(os.path.join(directory, filename), 'w') as f:
+            yaml.dump({k: getattr(self, k) for k in ('scale', 'rmin', 'rmax', 'z_width')}, f)
+
+    @classmethod
+    def from_yml(cls, directory, filename='GRID_Predictor_params.yml'):
+        """network.py:368-370."""
+        import yaml
+        with open(os.path.join(directory, filename)) as f:
+            return cls(**yaml.safe_load(f))
+
+
 # ------------------------------------------------------------------------------------------------
 # scene cache: the 9 frame-independent raytracing args are prepacked once per (arrays, predictor)
 # ------------------------------------------------------------------------------------------------
@@ -181,15 +279,15 @@ def _scene_for(predictor, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos,
 
 def _predictor_of(predictor_fn):
     p = getattr(predictor_fn, '__self__', predictor_fn)
-    if not isinstance(p, NeRF_Predictor):
-        raise TypeError('predictor_fn must be NeRF_Predictor.apply (GRID_Predictor is out of scope, SURVEY s2 #8)')
+    if not isinstance(p, (NeRF_Predictor, GRID_Predictor)):
+        raise TypeError('predictor_fn must be NeRF_Predictor.apply or GRID_Predictor.apply')
     return p
 
 
-def _flat(params, device):
+def _flat(params, device, pred=None):
     if isinstance(params, torch.Tensor):
         return params
-    return torch.as_tensor(flatten_params(params), device=device)
+    return torch.as_tensor((pred._flatten if pred is not None else flatten_params)(params), device=device)
 
 
 def _shape_images(images, scene, J):
@@ -208,7 +306,7 @@ def image_plane_prediction(params, predictor_fn, t_frames, coords, Omega, J, g, 
     pred = _predictor_of(predictor_fn)
     scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units)
     tf = np.atleast_1d(utils.time_value(t_frames, t_units)).astype(np.float32) if not isinstance(t_frames, torch.Tensor) else t_frames
-    images, _, _ = engine.render_fwd(scene, _flat(params, scene.device), tf, impl)
+    images, _, _ = pred._render_fwd(scene, _flat(params, scene.device, pred), tf, impl)
     return _shape_images(images, scene, J)
 
 
@@ -226,7 +324,7 @@ def loss_fn_image(params, predictor_fn, target, sigma, offset, t_frames, coords,
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
                          scene.device).reshape(-1)
     tgt, sig, off = _image_targets(scene, target, sigma, offset, dtype, tf.numel())
-    images, _, _ = engine.render_fwd(scene, _flat(params, scene.device), tf, impl)
+    images, _, _ = pred._render_fwd(scene, _flat(params, scene.device, pred), tf, impl)
     loss, _ = engine.loss_image(images, tgt, sig, off, float(scale), dtype)
     return loss, [_shape_images(images, scene, J)]
 
@@ -262,7 +360,7 @@ def loss_fn_eht(params, predictor_fn, target, sigma, A, t_frames, coords, Omega,
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
                          scene.device).reshape(-1)
     A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
-    images, _, _ = engine.render_fwd(scene, _flat(params, scene.device), tf, impl)
+    images, _, _ = pred._render_fwd(scene, _flat(params, scene.device, pred), tf, impl)
     vis = engine.vis_fwd(A, images)
     loss, _ = engine.loss_vis(vis, target, sigma, float(scale), dtype)
     return loss, [_shape_images(images, scene, J)]
@@ -298,7 +396,12 @@ def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, 
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
                          scene.device).reshape(-1)
     tgt, sig, off = _image_targets(scene, target, sigma, offset, dtype, tf.numel())
-    loss, images, grads = engine.train_step_image(scene, state.flat, tf, tgt, sig, off, float(scale), dtype, impl)
+    if isinstance(pred, GRID_Predictor):       # voxel grid: forward -> loss head -> pull-back to the grid (csrc/grid.cu)
+        images, _, _ = pred._render_fwd(scene, state.flat, tf)
+        loss, dI = engine.loss_image(images, tgt, sig, off, float(scale), dtype)
+        grads = pred._render_bwd(scene, state.flat, tf, dI)
+    else:
+        loss, images, grads = engine.train_step_image(scene, state.flat, tf, tgt, sig, off, float(scale), dtype, impl)
     state = _pmean_and_apply(state, grads)
     return loss, state, _shape_images(images, scene, J)
 
@@ -322,17 +425,17 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
     A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
     # the chi^2 is separable per frame: process frame chunks whose saved activations fit the workspace cap
     Bt = tf.numel()
-    Bc = engine.frames_per_chunk(scene, Bt, impl)
+    Bc = Bt if isinstance(pred, GRID_Predictor) else engine.frames_per_chunk(scene, Bt, impl)
     tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
     sig = engine._dev_f32(sigma, scene.device)
     loss, grads, imgs = None, None, []
     for b0 in range(0, Bt, Bc):
         sl = slice(b0, min(b0 + Bc, Bt))
-        images, e, acts = engine.render_fwd(scene, state.flat, tf[sl], impl, save_acts=True)
+        images, e, acts = pred._render_fwd(scene, state.flat, tf[sl], impl, save_acts=not isinstance(pred, GRID_Predictor))
         vis = engine.vis_fwd(A[sl].contiguous(), images)
         l, dvis = engine.loss_vis(vis, tgt[sl], sig[sl], float(scale), dtype)
         dI = engine.vis_bwd(A[sl].contiguous(), dvis, scene.P)
-        g = engine.render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)
+        g = pred._render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)
         loss = l if loss is None else engine.add_inplace(loss, l)       # per-chunk partials accumulate on the device
         grads = g if grads is None else engine.add_inplace(grads, g)
         imgs.append(images)

@@ -214,7 +214,7 @@ def restore_checkpoint(checkpoint_dir, state):
     with open(os.path.join(checkpoint_dir, 'checkpoint_%d' % ck[-1]), 'rb') as f:
         d = pickle.load(f)
     dev = state.flat.device
-    state.flat.copy_(torch.as_tensor(network.flatten_params(d['params']), device=dev))
+    state.flat.copy_(torch.as_tensor(state.predictor._flatten(d["params"]), device=dev))
     state.mu.copy_(torch.as_tensor(d['mu'], device=dev)); state.nu.copy_(torch.as_tensor(d['nu'], device=dev))
     state.step = int(d['step'])
     return state

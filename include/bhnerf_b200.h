@@ -142,6 +142,26 @@ int bhnerf_radiative_transfer(const float* emission, const float* g, const float
                               const float* Sigma, int32_t R, int32_t P, int32_t G, float* out,
                               void* stream);
 
+/* ---- grid renderers: the same warp + ray integral with a trilinear voxel lookup instead of the MLP.
+ * mode 0 = emission.image_plane_dynamics (bhnerf/emission.py:234-303: velocity_warp_coords -> interpolate_coords
+ *   :213-232 [utils.world_to_image_coords utils.py:160-166 + scipy map_coordinates order=1, cval=0: exactly 0
+ *   outside the grid extent] -> J broadcast -> kgeo.radiative_trasfer); samples before injection (NaN coordinates
+ *   in the reference, never reached by its callers) contribute 0.
+ * mode 1 = network.GRID_Predictor.__call__ (bhnerf/network.py:306-352) + image_plane_prediction: lookup with
+ *   fov = 2*scale per axis and jax.scipy.ndimage.map_coordinates' corner-wise cval blending, sigmoid(v - 10), domain
+ *   fill (from the prepack), injection mask.
+ * `scene` = bhnerf_prepack of the geodesics (for mode 0 prepack with rmin = 0 and rmax / z_width large enough to
+ * cover the grid: culled samples contribute exactly 0 either way).  grid [nx,ny,nz] fp32, voxel centres spanning
+ * [-fov/2, fov/2] per axis.  images [Bt,S,P] overwritten; e_out [Bt,n_pad] or NULL (per-sample emission).
+ * grid_render_bwd (mode 1): d_grid [nx,ny,nz] OVERWRITTEN with the pull-back of d_images [Bt,S,P] to the grid
+ * (jax.value_and_grad w.r.t. params['grid'], network.py:617).                                                  */
+int bhnerf_grid_render_fwd(const bhnerf_scene_t* scene, const float* grid, int32_t nx, int32_t ny,
+                           int32_t nz, float fov_x, float fov_y, float fov_z, int32_t mode,
+                           const float* t_frames, int32_t Bt, float* images, float* e_out, void* stream);
+int bhnerf_grid_render_bwd(const bhnerf_scene_t* scene, const float* grid, int32_t nx, int32_t ny,
+                           int32_t nz, float fov_x, float fov_y, float fov_z, const float* t_frames,
+                           int32_t Bt, const float* d_images, float* d_grid, void* stream);
+
 /* ---- optimiser: optax.adam + polynomial_schedule(power=1) applied by
  * TrainState.apply_gradients (bhnerf/network.py:171-182, :621).  grad_scale multiplies the
  * gradient first (1/ndev turns an all-reduce SUM into jax.lax.pmean, network.py:620).

@@ -391,3 +391,51 @@ def image_plane_dynamics(emission_0, grid_fov, rt, t_frames, GM_c3=GM_C3_SGRA_HR
         e = np.asarray(J)[None] * e[:, None]
     g, dtau, Sigma = [np.asarray(rt[k], dtype=np.float64) for k in ('g', 'dtau', 'Sigma')]
     return (g ** 2 * e * dtau * Sigma).sum(axis=-1)
+
+
+# --------------------------------------------------------------------------------------
+# GRID_Predictor (bhnerf/network.py:254-357): voxel grid + jax.scipy.ndimage.map_coordinates
+# --------------------------------------------------------------------------------------
+def jax_map_coordinates_order1(grid, ic):
+    """jax.scipy.ndimage.map_coordinates(grid, ic, order=1, mode='constant', cval=0) restated in torch
+    (jax/_src/scipy/ndimage.py, published algorithm; jax is not installed): per axis the two neighbours
+    floor(c), floor(c)+1 with weights 1-frac, frac; a neighbour outside [0, n) contributes cval (0)
+    -- corner by corner, unlike scipy's 'constant' mode which returns cval for any point outside the extent.
+    grid: torch (nx,ny,nz); ic: torch (3, ...).  Differentiable w.r.t. grid."""
+    n = grid.shape
+    lo = torch.floor(ic)
+    fr = ic - lo
+    lo = lo.long()
+    out = torch.zeros(ic.shape[1:], dtype=grid.dtype)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                idx = [lo[0] + dx, lo[1] + dy, lo[2] + dz]
+                ok = torch.ones_like(out, dtype=torch.bool)
+                w = torch.ones_like(out)
+                for a, d in enumerate((dx, dy, dz)):
+                    ok &= (idx[a] >= 0) & (idx[a] < n[a])
+                    w = w * (fr[a] if d else 1 - fr[a])
+                val = grid[idx[0].clamp(0, n[0] - 1), idx[1].clamp(0, n[1] - 1), idx[2].clamp(0, n[2] - 1)]
+                out = out + torch.where(ok, val, torch.zeros_like(val)) * w
+    return out
+
+
+def grid_predictor_images(grid, t_frames, rt, predictor, GM_c3=GM_C3_SGRA_HR, dtype=torch.float64):
+    """GRID_Predictor.__call__ + image_plane_prediction (network.py:306-357, 373-420).  grid: torch tensor
+    (res,res,res) (requires_grad allowed).  Returns images (nt, [S,] A, B) as a torch tensor."""
+    coords = _t(rt['coords'], dtype)
+    warped = velocity_warp_coords(rt['coords'], rt['Omega'], t_frames, rt['t_start_obs'], rt['t_geos'],
+                                  rt['t_injection'], GM_c3, dtype)                       # (nt, ..., 3), NaN before injection
+    valid = torch.isfinite(warped)
+    net_in = torch.where(valid, warped, torch.zeros_like(warped)).movedim(-1, 0)
+    res = grid.shape[0]
+    net_in = (net_in + predictor['scale']) / (2 * predictor['scale']) * (res - 1.0)
+    e = torch.sigmoid(jax_map_coordinates_order1(grid, net_in) - 10.0)
+    e = fill_unsupervised_emission(e, coords, predictor['rmin'], predictor['rmax'], predictor['z_width'])
+    e = torch.where(valid[..., 0], e, torch.zeros_like(e))
+    J = rt['J']
+    if not np.isscalar(J):
+        e = _t(J, dtype)[None] * e[:, None]
+    g, dtau, Sigma = [_t(rt[k], dtype) for k in ('g', 'dtau', 'Sigma')]
+    return (g ** 2 * e * dtau * Sigma).sum(-1)

@@ -313,3 +313,85 @@ def test_fp16_operand_overflow_is_flagged_not_hidden():
         engine.workspace_status(impl='tc')
     engine.render_fwd(scene, good, tf, 'tc')  # flags are per step
     assert engine.workspace_status(impl='tc')[3] == 0
+
+
+def _geo_ns(geo, with_g=True):
+    import types
+    ns = types.SimpleNamespace(x=geo['coords'][0], y=geo['coords'][1], z=geo['coords'][2], t=geo['t_geos'],
+                               dtau=geo['dtau'], Sigma=geo['Sigma'])
+    if with_g:
+        ns.g = geo['g']
+    return ns
+
+
+def test_image_plane_dynamics_vs_reference_and_oracle():
+    """emission.image_plane_dynamics (csrc/grid.cu, mode 0) against the output of the reference's own function
+    (doppler=False) and against the float64 oracle with Doppler factor, Stokes factors and pre-injection frames."""
+    from bhnerf_b200 import constants, emission
+    d = np.load(os.path.join(G, 'grid_dynamics.npz'))
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    tfM = (d['t_frames'] - float(d['t_start_obs'])) / float(d['GM_c3'])        # plain numbers = units of M (reference)
+    fov = float(d['fov'])
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    out = emission.image_plane_dynamics(d['emission_0'], _geo_ns(geo), geo['Omega'], tfM, float(d['t_injection']),
+                                        t_start_obs=0.0, doppler=False, fov=fov).cpu().numpy()
+    assert out.shape == d['ref_images'].shape and rel(out, d['ref_images']) < IMG_TOL, rel(out, d['ref_images'])
+    out = emission.image_plane_dynamics(d['emission_0'], _geo_ns(geo), geo['Omega'], tfM, float(d['t_injection']),
+                                        t_start_obs=0.0, fov=fov).cpu().numpy()
+    assert rel(out, d['images_g']) < IMG_TOL, rel(out, d['images_g'])
+    out = emission.image_plane_dynamics(d['emission_0'], _geo_ns(geo), geo['Omega'], tfM, float(d['t_injection']),
+                                        J=d['J'], t_start_obs=0.0, fov=fov).cpu().numpy()
+    assert out.shape == d['images_J'].shape and rel(out, d['images_J']) < IMG_TOL, rel(out, d['images_J'])
+    # hours + t_units (same conversion as the train path), frames before injection render 0
+    out = emission.image_plane_dynamics(d['emission_0'], _geo_ns(geo), geo['Omega'], d['t_frames'],
+                                        float(d['t_injection_early']), t_start_obs=float(d['t_start_early']), fov=fov,
+                                        t_units='hr').cpu().numpy()
+    assert abs(constants.GM_c3(t_units='hr') - float(d['GM_c3'])) < 1e-9
+    assert rel(out, d['images_early']) < IMG_TOL and (out[0] == 0).all(), rel(out, d['images_early'])
+    # a movie of grids: (T, nt, A, B) as in the reference
+    mov = np.stack([d['emission_0'], 2.0 * d['emission_0']])
+    out = emission.image_plane_dynamics(mov, _geo_ns(geo), geo['Omega'], tfM, float(d['t_injection']), t_start_obs=0.0,
+                                        fov=fov).cpu().numpy()
+    assert out.shape == (2,) + d['images_g'].shape and rel(out[1], 2.0 * d['images_g']) < IMG_TOL
+
+
+def test_grid_predictor_forward_loss_gradient_and_step_vs_oracle():
+    """network.GRID_Predictor through the reference-facing API: images, 'full' loss, gradient w.r.t. the grid
+    (pull-back kernel, atomics) and one optax-Adam update, against the float64 oracle golden."""
+    from bhnerf_b200 import engine, network
+    from oracle import bhnerf_oracle as O
+    d = np.load(os.path.join(G, 'grid_predictor.npz'))
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    pred = network.GRID_Predictor(float(d['scale']), float(d['rmin']), float(d['rmax']), float(d['z_width']),
+                                  grid_res=d['grid'].shape[0])
+    assert (pred.init_params()['grid'] == -10).all()
+    rta = network.raytracing_args(_geo_ns(geo), geo['Omega'], float(d['t_injection']), float(d['t_start_obs']))
+    params = {'grid': d['grid']}
+    rel = lambda a, b: float(np.abs(np.asarray(a) - b).max() / np.abs(b).max())
+    img = network.image_plane_prediction(params, pred.apply, d['t_frames'], *rta.values(), 'hr').cpu().numpy()
+    assert rel(img, d['images']) < IMG_TOL, rel(img, d['images'])
+    rtaJ = network.raytracing_args(_geo_ns(geo), geo['Omega'], float(d['t_injection']), float(d['t_start_obs']), J=d['J'])
+    imgJ = network.image_plane_prediction(params, pred.apply, d['t_frames'], *rtaJ.values(), 'hr').cpu().numpy()
+    assert imgJ.shape == d['images_J'].shape and rel(imgJ, d['images_J']) < IMG_TOL
+    sig = np.ones_like(d['target']); off = np.zeros_like(d['target'])
+    loss, _ = network.loss_fn_image(params, pred.apply, d['target'], sig, off, d['t_frames'], *rta.values(), 1.0, 'hr', 'full')
+    assert abs(loss.item() - float(d['loss'])) / float(d['loss']) < IMG_TOL
+    state = pred.init_state(params, num_iters=100, lr_init=1e-2, lr_final=1e-4)
+    scene = network._scene_for(pred, *rta.values(), 'hr', device=state.flat.device)
+    tf = torch.as_tensor(d['t_frames'].astype(np.float32)).cuda()
+    images, _, _ = pred._render_fwd(scene, state.flat, tf)
+    _, dI = engine.loss_image(images, d['target'].reshape(4, -1), sig.reshape(4, -1), off.reshape(4, -1), 1.0, 'full')
+    g = pred._render_bwd(scene, state.flat, tf, dI).cpu().numpy().reshape(d['grad'].shape)
+    assert rel(g, d['grad']) < GRAD_TOL, rel(g, d['grad'])
+    assert ((g != 0) == (d['grad'] != 0)).mean() > 0.999
+    l2, state, _ = network.gradient_step_image(state, 'hr', 'full', d['target'], sig, off, d['t_frames'], *rta.values(), 1.0)
+    want, _, _ = O.adam_step(d['grid'].reshape(-1).astype(np.float64), d['grad'].reshape(-1), np.zeros(d['grid'].size),
+                             np.zeros(d['grid'].size), 0, 1e-2, 1e-4, 100)
+    got = state.flat.cpu().numpy().astype(np.float64)
+    moved = d['grad'].reshape(-1) != 0
+    assert np.abs(got - want)[moved].max() / 1e-2 < 2e-3 and state.step == 1
+    assert abs(l2.item() - float(d['loss'])) / float(d['loss']) < IMG_TOL
+    # GRID_Predictor.apply: dense emission on the geodesic points, zero outside the domain / before injection
+    e = pred.apply({'params': params}, d['t_frames'], 'hr', geo['coords'], geo['Omega'], float(d['t_start_obs']),
+                   geo['t_geos'], float(d['t_injection']))
+    assert e.shape == (4,) + geo['coords'].shape[1:] and (e[0] == 0).all() and 0 < e.max() <= 1

@@ -146,3 +146,44 @@ def test_oracle_vs_reference_source_live(geo):
     np.testing.assert_array_equal(
         O.fill_unsupervised_emission(torch.as_tensor(e), torch.as_tensor(co), 2.5, 7.0, 3.0).numpy(),
         ns.emission.fill_unsupervised_emission(e, co, 2.5, 7.0, 3.0, use_jax=True))
+
+
+def test_image_plane_dynamics_oracle_vs_reference_golden():
+    """oracle.image_plane_dynamics against the output of the reference's OWN emission.image_plane_dynamics
+    (tests/golden/grid_dynamics.npz:ref_images, generated by make_golden_grid.py under the numpy shim)."""
+    d = np.load(os.path.join(G, 'grid_dynamics.npz'))
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    rt = dict(coords=geo['coords'], Omega=geo['Omega'], dtau=geo['dtau'], Sigma=geo['Sigma'], t_geos=geo['t_geos'],
+              t_start_obs=float(d['t_start_obs']), t_injection=float(d['t_injection']), g=np.ones_like(geo['g']), J=1.0)
+    out = O.image_plane_dynamics(d['emission_0'].astype(np.float64), float(d['fov']), rt, d['t_frames'])
+    assert np.abs(out - d['ref_images']).max() / np.abs(d['ref_images']).max() < 1e-6       # grid stored as float32
+    assert np.abs(d['ref_images']).max() > 0.1
+
+
+def test_jax_map_coordinates_restatement():
+    """Known answers of jax.scipy.ndimage.map_coordinates(order=1, cval=0): equals scipy inside the grid, and blends
+    with cval corner by corner up to one cell outside (where scipy's 'constant' mode already returns cval)."""
+    import scipy.ndimage
+    import torch
+    rng = np.random.default_rng(0)
+    grid = rng.normal(size=(5, 6, 7))
+    pts = rng.uniform(0, 4, size=(3, 50)); pts[1] *= 5 / 4; pts[2] *= 6 / 4
+    ours = O.jax_map_coordinates_order1(torch.as_tensor(grid), torch.as_tensor(pts)).numpy()
+    np.testing.assert_allclose(ours, scipy.ndimage.map_coordinates(grid, pts, order=1, cval=0.0), rtol=1e-12, atol=1e-14)
+    edge = torch.tensor([[-0.25, 4.5, -1.0, 2.0], [0.0, 0.0, 0.0, 5.75], [0.0, 0.0, 0.0, 6.5]], dtype=torch.float64)
+    got = O.jax_map_coordinates_order1(torch.as_tensor(grid), edge).numpy()
+    want = [0.75 * grid[0, 0, 0], 0.5 * grid[4, 0, 0], 0.0, 0.25 * 0.5 * grid[2, 5, 6]]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+    assert scipy.ndimage.map_coordinates(grid, edge[:, :1].numpy(), order=1, cval=0.0)[0] == 0.0
+
+
+def test_grid_predictor_oracle_golden_is_reproducible():
+    import torch
+    d = np.load(os.path.join(G, 'grid_predictor.npz'))
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    rt = dict(coords=geo['coords'], Omega=geo['Omega'], dtau=geo['dtau'], Sigma=geo['Sigma'], t_geos=geo['t_geos'],
+              g=geo['g'], J=1.0, t_start_obs=float(d['t_start_obs']), t_injection=float(d['t_injection']))
+    pred = {k: float(d[k]) for k in ('scale', 'rmin', 'rmax', 'z_width')}
+    img = O.grid_predictor_images(torch.as_tensor(d['grid'].astype(np.float64)), d['t_frames'], rt, pred).numpy()
+    np.testing.assert_allclose(img, d['images'], rtol=1e-10, atol=1e-12)
+    assert (img[0] == 0).all() and img[-1].max() > 1.0        # first frame is entirely before injection

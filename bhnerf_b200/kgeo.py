@@ -54,3 +54,41 @@ def doppler_factor(geos, umu, fillna=0.0):
     if not ((isinstance(fillna, bool) and fillna is False) or fillna is None):
         g = np.where(np.isnan(g), fillna, g)
     return g
+
+
+def geodesic_inputs(geos, Omega=None, omega_sign=None, fillna=0.0, device=None):
+    """Tracer output -> the geometry entries of network.raytracing_args, on the GPU (C ABI: bhnerf_geodesic_inputs).
+    ``geos``: mapping / namespace with float64 r, theta, phi, t, mino of shape (*img, G), ``lam`` (per ray, shape *img
+    or broadcastable (*img, G)), ``spin`` and optionally ``M``.  ``Omega=None`` selects the Keplerian field
+    sign(spin + eps) sqrt(M) / (r^1.5 + spin sqrt(M)) (Tutorial3 cell 2); an array is used as given.
+    Returns a dict of float32 device tensors: coords (3,*img,G), Omega, g, dtau, Sigma, t_geos (*img,G)."""
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else 'cuda')
+    f64 = lambda a: torch.as_tensor(np.array(a, dtype=np.float64, order='C'), device=dev)
+    r = f64(_get(geos, 'r'))
+    shape = tuple(r.shape)
+    G = shape[-1]
+    P = int(np.prod(shape[:-1]))
+    th, ph, t, mino = [f64(_get(geos, k)).reshape(P, G).contiguous() for k in ('theta', 'phi', 't', 'mino')]
+    lam = np.asarray(_get(geos, 'lam'), dtype=np.float64)
+    lam = np.broadcast_to(lam, shape)[..., 0] if lam.ndim == len(shape) else np.broadcast_to(lam, shape[:-1])
+    lam = f64(lam).reshape(P).contiguous()
+    a = float(_get(geos, 'spin'))
+    try:
+        M = float(_get(geos, 'M'))
+    except (KeyError, AttributeError):
+        M = 1.0
+    Om_in = None if Omega is None else f64(np.broadcast_to(np.asarray(Omega, dtype=np.float64), shape)).reshape(P, G).contiguous()
+    if omega_sign is None:
+        omega_sign = float(np.sign(a + np.finfo(float).eps))
+    out = {k: torch.empty((P, G), dtype=torch.float32, device=dev) for k in ('Omega', 'g', 'dtau', 'Sigma', 't_geos')}
+    coords = torch.empty((3, P, G), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_geodesic_inputs(engine._ptr(r.reshape(P, G).contiguous()), engine._ptr(th), engine._ptr(ph),
+                                         engine._ptr(t), engine._ptr(mino), engine._ptr(lam), engine._ptr(Om_in), P, G, a, M,
+                                         float(omega_sign), float(fillna), engine._ptr(coords), engine._ptr(out['Omega']),
+                                         engine._ptr(out['g']), engine._ptr(out['dtau']), engine._ptr(out['Sigma']),
+                                         engine._ptr(out['t_geos']), engine._stream()))
+    res = {k: v.reshape(shape) for k, v in out.items()}
+    res['coords'] = coords.reshape((3,) + shape)
+    return res

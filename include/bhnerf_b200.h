@@ -162,6 +162,18 @@ int bhnerf_grid_render_bwd(const bhnerf_scene_t* scene, const float* grid, int32
                            int32_t nz, float fov_x, float fov_y, float fov_z, const float* t_frames,
                            int32_t Bt, const float* d_images, float* d_grid, void* stream);
 
+/* ---- geodesic post-processing (setup, once per (spin, inclination)): tracer output -> the arrays of
+ * network.raytracing_args.  Fuses Geodesics.get_dataset's algebra (kgeo/kgeo/kerr_raytracing_utils.py:220-279:
+ * x,y,z, Sigma, dtau = concat(0, diff(mino))), the Keplerian angular velocity (Tutorial3 cell 2, alma.py:49) when
+ * Omega_in is NULL (omega_sign = +-1 sets the rotation sense), and kgeo.azimuthal_velocity_vector + doppler_factor
+ * (bhnerf/kgeo.py:199-248; NaN -> fillna).  Inputs float64 [P,G] (lam [P], per ray), outputs float32:
+ * coords [3,P,G], Omega, g, dtau, Sigma, t_geos [P,G].                                                            */
+int bhnerf_geodesic_inputs(const double* r, const double* theta, const double* phi, const double* t,
+                           const double* mino, const double* lam, const double* Omega_in, int64_t P,
+                           int32_t G, double spin, double M, double omega_sign, double fillna,
+                           float* coords, float* Omega, float* g, float* dtau, float* Sigma,
+                           float* t_geos, void* stream);
+
 /* ---- optimiser: optax.adam + polynomial_schedule(power=1) applied by
  * TrainState.apply_gradients (bhnerf/network.py:171-182, :621).  grad_scale multiplies the
  * gradient first (1/ndev turns an all-reduce SUM into jax.lax.pmean, network.py:620).

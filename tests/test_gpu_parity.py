@@ -395,3 +395,31 @@ def test_grid_predictor_forward_loss_gradient_and_step_vs_oracle():
     e = pred.apply({'params': params}, d['t_frames'], 'hr', geo['coords'], geo['Omega'], float(d['t_start_obs']),
                    geo['t_geos'], float(d['t_injection']))
     assert e.shape == (4,) + geo['coords'].shape[1:] and (e[0] == 0).all() and 0 < e.max() <= 1
+
+
+def test_geodesic_inputs_vs_reference_algebra():
+    """kgeo.geodesic_inputs (bhnerf_geodesic_inputs: get_dataset algebra + Keplerian Omega + Doppler factor, float64
+    on the GPU) against the arrays the reference's own tracer + algebra produced (kerr_a0.2_i60_16x16x32.npz)."""
+    from bhnerf_b200 import kgeo
+    raw = np.load(os.path.join(G, 'kerr_raw_a0.2_i60_16x16x32.npz'))
+    ref = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    geos = {k: raw[k] for k in ('r', 'theta', 'phi', 't', 'mino', 'lam')}
+    geos.update(spin=float(raw['spin']), M=float(raw['M']))
+    out = kgeo.geodesic_inputs(geos)
+    for k, want in (('coords', ref['coords']), ('Omega', ref['Omega']), ('g', ref['g']), ('dtau', ref['dtau']),
+                    ('Sigma', ref['Sigma']), ('t_geos', ref['t_geos'])):
+        got = out[k].cpu().numpy()
+        assert got.shape == want.shape, k
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6 * np.abs(want).max(), err_msg=k)
+    assert (out['g'].cpu().numpy() == 0).sum() == (ref['g'] == 0).sum() > 0          # NaN -> 0 where no circular orbit
+    # a user-supplied velocity field is taken as given (here: the Keplerian one, in float64)
+    Om = np.sign(0.2) / (raw['r'] ** 1.5 + 0.2)
+    out2 = kgeo.geodesic_inputs(geos, Omega=Om)
+    assert torch.equal(out2['g'], out['g']) and torch.equal(out2['Omega'], out['Omega'])
+    # the result feeds the prepack directly
+    from bhnerf_b200 import engine, constants
+    scene = engine.PackedScene(out['coords'], out['Omega'], 1.0, out['g'], out['dtau'], out['Sigma'], out['t_geos'], 0.0,
+                               -1000.0, 8.0, 2.5, 8.0, 4.0, constants.GM_c3(t_units='hr'))
+    scene_ref = engine.PackedScene(ref['coords'], ref['Omega'], 1.0, ref['g'], ref['dtau'], ref['Sigma'], ref['t_geos'], 0.0,
+                                   -1000.0, 8.0, 2.5, 8.0, 4.0, constants.GM_c3(t_units='hr'))
+    assert scene.n_active == scene_ref.n_active > 0

@@ -221,8 +221,14 @@ static size_t train_frame_bytes(const bhnerf_scene_t* sc, int impl, int pl) {
 }
 extern "C" size_t bhnerf_train_workspace_bytes(const bhnerf_scene_t* sc, int32_t Bt, int32_t impl) {
   // all Bt frames in one chunk; smaller workspaces are accepted down to one frame
-  const int pl = bh_tc_planes(sc->n_active, Bt);
-  return bwd_fixed_bytes(impl, pl) + train_frame_bytes(sc, impl, pl) * (size_t)Bt + 1024;
+  // large enough for either precision plan the step may pick (it depends on the loss kind, bhnerf_train_step_image)
+  size_t need = 0;
+  const int plans[2] = {bh_tc_planes(sc->n_active, Bt), bh_tc_planes_full_loss(sc->n_active, Bt)};
+  for (int pl : plans) {
+    size_t b = bwd_fixed_bytes(impl, pl) + train_frame_bytes(sc, impl, pl) * (size_t)Bt + 1024;
+    if (b > need) need = b;
+  }
+  return need;
 }
 
 int bh_loss_image_accum(const float* images, const float* target, const float* sigma, const float* offset,
@@ -241,7 +247,8 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
   PackedView v = bh_view(sc);
   FrameConsts fc = frame_consts(sc);
   char* ws = (char*)workspace;
-  const int pl = bh_tc_planes(sc->n_active, Bt);
+  // the fused step owns its workspace layout, so its precision plan may depend on the loss (render_tc.cu)
+  const int pl = kind == BHNERF_LOSS_FULL ? bh_tc_planes_full_loss(sc->n_active, Bt) : bh_tc_planes(sc->n_active, Bt);
   size_t fixed = bwd_fixed_bytes(impl, pl);
   size_t per_frame = train_frame_bytes(sc, impl, pl);
   BH_REQUIRE(workspace_bytes >= fixed + per_frame, "train_step_image: workspace (%zu B) cannot hold one frame (%zu B)",

@@ -143,6 +143,7 @@ int bh_simt_bwd(const PackedView& v, const float* params, const float* d_images 
 
 // TC (tcgen05) family.  `planes` = bf16 planes kept of every saved activation / cotangent (1: hi, 2: hi+lo).
 int bh_tc_planes(int n_active, int Bt_total);               // precision plan of a step
+int bh_tc_planes_full_loss(int n_active, int Bt_total);     // ... of the fused step with the per-pixel image loss
 size_t bh_tc_acts_bytes_per_frame(int n_pad, int planes);
 size_t bh_tc_delta_bytes_per_frame(int n_pad, int planes); // backward scratch (delta images), 0 with the fused backward
 size_t bh_tc_delta_fixed_bytes(int planes);                  // delta ring of the fused backward (frame-count independent)

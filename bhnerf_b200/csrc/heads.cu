@@ -299,6 +299,48 @@ extern "C" int bhnerf_adam_step(float* params, const float* grads, float* mu, fl
   return 0;
 }
 
+// Same update with the step counter in DEVICE memory, so that a whole train step (render -> loss -> gradient ->
+// Adam) can be captured once in a CUDA graph and replayed: the schedule and the bias corrections are derived from
+// *count_dev inside the kernel (double precision, one thread per block), and a second one-thread kernel advances it.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
+                                float* __restrict__ nu, int n, const int* __restrict__ count_dev, float lr_init,
+                                float lr_final, int transition_steps, float b1, float b2, float eps, float gscale) {
+  __shared__ float sh[3];
+  if (threadIdx.x == 0) {
+    const int count = *count_dev;
+    const int c = count < 0 ? 0 : (count > transition_steps ? transition_steps : count);
+    const double frac = 1.0 - (double)c / (double)transition_steps;
+    sh[0] = (float)((double)(lr_init - lr_final) * frac + (double)lr_final);
+    const double t = (double)count + 1.0;
+    sh[1] = (float)(1.0 - pow((double)b1, t));
+    sh[2] = (float)(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const float lr = sh[0], bc1 = sh[1], bc2 = sh[2];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * gscale;
+  float m = b1 * mu[i] + (1.f - b1) * gi;
+  float v = b2 * nu[i] + (1.f - b2) * gi * gi;
+  mu[i] = m; nu[i] = v;
+  float mh = m / bc1, vh = v / bc2;
+  p[i] = p[i] - lr * mh / (sqrtf(vh) + eps);
+}
+__global__ void counter_inc_kernel(int* c) { *c += 1; }
+
+extern "C" int bhnerf_adam_step_dev(float* params, const float* grads, float* mu, float* nu, int32_t n,
+                                    int32_t* count_dev, float lr_init, float lr_final, int32_t transition_steps,
+                                    float b1, float b2, float eps, float grad_scale, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_REQUIRE(transition_steps > 0 && count_dev, "adam_dev: transition_steps must be > 0 and count_dev non-NULL");
+  BhProfScope ps(BH_CAT_MISC, 2, st);
+  adam_dev_kernel<<<(n + 255) / 256, 256, 0, st>>>(params, grads, mu, nu, n, count_dev, lr_init, lr_final, transition_steps,
+                                                   b1, b2, eps, grad_scale);
+  counter_inc_kernel<<<1, 1, 0, st>>>(count_dev);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // stand-alone dense stages (the reference exposes them as public functions; inside the render
 // kernels they are fused).  Elementwise / short reductions, HBM-bound.

@@ -578,6 +578,18 @@ size_t bh_tc_acts_bytes_per_frame(int n_pad, int planes) { return tc_acts_bytes_
 // only, the rounding noise of the wgrad reduction averages out as 1/sqrt(#sample-frames) (measured 1e-4 of the
 // gradient at 4.5e6 sample-frames); below 2^19 sample-frames per step both planes are kept (x3 products, error
 // ~1e-5 at any size).  BHNERF_TC_PLANES=1|2 overrides.
+// Per-pixel image loss ('full'): every pixel's residual enters the gradient with its own sign-stable weight, there is
+// no cancellation between rays, and the one-plane noise is 3.0e-4 of the gradient already at 1.1e4 sample-frames
+// (6e-5 at 5.9e4; scripts/planes_study.py) -- against 6e-3 / 2e-3 for the lightcurve and closure-phase losses, whose
+// gradients are small differences of large per-ray terms.  The fused image step may therefore drop to one plane 16x
+// earlier for 'full'.
+int bh_tc_planes_full_loss(int n_active, int Bt_total) {
+  int base = bh_tc_planes(n_active, Bt_total);
+  if (base == 1) return 1;
+  const char* e = getenv("BHNERF_TC_PLANES");
+  if (e && (e[0] == '1' || e[0] == '2')) return base;
+  return ((long long)n_active * (long long)Bt_total < (1ll << 15)) ? 2 : 1;
+}
 int bh_tc_planes(int n_active, int Bt_total) {
   static int forced = -1;
   if (forced < 0) {

@@ -386,6 +386,108 @@ def _pmean_and_apply(state, grads, update=True):
     return state
 
 
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the whole train step.  The reference's training loops run tiny steps (batchsize 6 of a 64x64
+# image plane: ~0.3 ms of GPU work) tens of thousands of times; host dispatch of the ~10 launches of a step costs more
+# than the step.  Every C-ABI call only enqueues on the stream and the Adam step counter lives in device memory
+# (bhnerf_adam_step_dev), so the sequence [train_step_image -> adam] is captured once per (state, scene, batch shape)
+# and replayed; the per-step inputs travel in ONE pinned-host -> device copy.  BHNERF_CUDA_GRAPHS=0 disables it.
+# ------------------------------------------------------------------------------------------------
+_USE_GRAPHS = os.environ.get('BHNERF_CUDA_GRAPHS', '1') != '0'
+_graph_cache = OrderedDict()
+
+
+class _GraphedImageStep:
+    N_STAGE = 4          # pinned staging buffers in rotation (a buffer is rewritten only after its copy completed)
+
+    def __init__(self, state, scene, Bt, kind, scale, impl):
+        dev = scene.device
+        self.Bt, self.kind = Bt, kind
+        self.n_t = Bt * scene.S * scene.P if kind == 'full' else Bt * scene.S
+        total = Bt + 3 * self.n_t
+        self.stage = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(self.N_STAGE)]
+        self.stage_np = [t.numpy() for t in self.stage]
+        self.stage_ev = [None] * self.N_STAGE
+        self.turn = 0
+        self.dev = torch.zeros(total, dtype=torch.float32, device=dev)
+        n = self.n_t
+        self.tf, self.tgt, self.sig, self.off = (self.dev[:Bt], self.dev[Bt:Bt + n], self.dev[Bt + n:Bt + 2 * n],
+                                                 self.dev[Bt + 2 * n:])
+        self.sig.fill_(1.0)
+        self.out = (torch.empty(1, dtype=torch.float32, device=dev),
+                    torch.empty((Bt, scene.S, scene.P), dtype=torch.float32, device=dev),
+                    torch.empty(engine.N_PARAMS, dtype=torch.float32, device=dev))
+        self.count = torch.full((1,), int(state.step), dtype=torch.int32, device=dev)
+        self.synced_step = int(state.step)
+        self.state, self.scene = state, scene          # keep the captured buffers alive
+        lib = engine._lib.load()
+
+        def body():
+            engine.train_step_image(scene, state.flat, self.tf, self.tgt, self.sig, self.off, float(scale), kind, impl,
+                                    out=self.out)
+            engine.check(lib.bhnerf_adam_step_dev(engine._ptr(state.flat), engine._ptr(self.out[2]), engine._ptr(state.mu),
+                                                  engine._ptr(state.nu), state.flat.numel(), engine._ptr(self.count),
+                                                  state.lr_init, state.lr_final, state.num_iters, 0.9, 0.999, 1e-8, 1.0,
+                                                  engine._stream()))
+        # warm-up outside the capture (lazy module load, function attributes, workspace growth), on saved copies so that
+        # it leaves the optimiser state untouched
+        keep = [t.clone() for t in (state.flat, state.mu, state.nu, self.count)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for t, k in zip((state.flat, state.mu, state.nu, self.count), keep):
+            t.copy_(k)
+        self.ws = engine._workspaces.get(dev.index if dev.index is not None else torch.cuda.current_device())
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def _fill(self, dst_np, dst_dev, src):
+        """numpy -> pinned staging (returns True), device tensor -> device slot directly (returns False)."""
+        if isinstance(src, torch.Tensor):
+            dst_dev.copy_(src.reshape(-1), non_blocking=True)
+            return False
+        np.copyto(dst_np, np.asarray(src, dtype=np.float32).reshape(-1))
+        return True
+
+    def run(self, state, tf, tgt, sig, off):
+        k = self.turn = (self.turn + 1) % self.N_STAGE
+        if self.stage_ev[k] is not None:
+            self.stage_ev[k].synchronize()
+        h, Bt, n = self.stage_np[k], self.Bt, self.n_t
+        host = [self._fill(h[:Bt], self.tf, tf), self._fill(h[Bt:Bt + n], self.tgt, tgt),
+                self._fill(h[Bt + n:Bt + 2 * n], self.sig, sig), self._fill(h[Bt + 2 * n:], self.off, off)]
+        if all(host):
+            self.dev.copy_(self.stage[k], non_blocking=True)
+        else:
+            for ok, (a, b) in zip(host, ((0, Bt), (Bt, Bt + n), (Bt + n, Bt + 2 * n), (Bt + 2 * n, Bt + 3 * n))):
+                if ok:
+                    self.dev[a:b].copy_(self.stage[k][a:b], non_blocking=True)
+        if any(host):
+            ev = self.stage_ev[k] = self.stage_ev[k] or torch.cuda.Event()
+            ev.record()
+        if int(state.step) != self.synced_step:           # restored checkpoint / external update of the counter
+            self.count.fill_(int(state.step))
+        self.graph.replay()
+        state.step += 1
+        self.synced_step = int(state.step)
+        return self.out[0].clone(), self.out[1].clone()
+
+
+def _graphed_image_step(state, scene, Bt, kind, scale, impl):
+    key = (id(state), state.flat.data_ptr(), id(scene), Bt, kind, float(scale), engine.resolve_impl(impl))
+    hit = _graph_cache.get(key)
+    if hit is None:
+        hit = _graph_cache[key] = _GraphedImageStep(state, scene, Bt, kind, scale, impl)
+        while len(_graph_cache) > 4:
+            _graph_cache.popitem(last=False)
+    else:
+        _graph_cache.move_to_end(key)
+    return hit
+
+
 def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, coords, Omega, J, g, dtau, Sigma,
                         t_start_obs, t_geos, t_injection, scale, impl=None):
     """bhnerf/network.py:566-622: value_and_grad(loss_fn_image) -> pmean -> apply_gradients.
@@ -393,6 +495,16 @@ def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, 
     pred = state.predictor
     scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units,
                        device=state.flat.device)
+    if _USE_GRAPHS and isinstance(pred, NeRF_Predictor) and _dist() is None and dtype in ('full', 'lc'):
+        tfh = t_frames if isinstance(t_frames, torch.Tensor) else np.atleast_1d(utils.time_value(t_frames, t_units))
+        Bt = int(tfh.numel() if isinstance(tfh, torch.Tensor) else tfh.size)
+        step = _graphed_image_step(state, scene, Bt, dtype, scale, impl)
+        want = step.n_t
+        for a in (target, sigma, offset):
+            if int(a.numel() if isinstance(a, torch.Tensor) else np.size(a)) != want:
+                raise AssertionError('target shape mismatch')
+        loss, images = step.run(state, tfh, target, sigma, offset)
+        return loss, state, _shape_images(images, scene, J)
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
                          scene.device).reshape(-1)
     tgt, sig, off = _image_targets(scene, target, sigma, offset, dtype, tf.numel())

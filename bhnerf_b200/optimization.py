@@ -116,7 +116,8 @@ class TemporalBatchedArgs(object):
         self.default_t_units = 'hr'
 
     def sample(self, batchsize, replace=False):
-        return _same_on_all_ranks(np.random.choice(range(self.num_frames), batchsize, replace=replace))
+        # same draw as the reference's np.random.choice(range(n), ...) for a given seed, without building the range
+        return _same_on_all_ranks(np.random.choice(self.num_frames, batchsize, replace=replace))
 
     def __getitem__(self, key):
         return [shard(arg[key, ...]) for arg in self.args]

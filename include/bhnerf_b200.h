@@ -184,6 +184,12 @@ int bhnerf_adam_step(float* params, const float* grads, float* mu, float* nu, in
                      int32_t count, float lr_init, float lr_final, int32_t transition_steps,
                      float b1, float b2, float eps, float grad_scale, void* stream);
 
+/* The same update with the step counter in device memory (*count_dev is read, then advanced by one): nothing in the
+ * call depends on host state, so a whole train step can be captured in a CUDA graph and replayed.                */
+int bhnerf_adam_step_dev(float* params, const float* grads, float* mu, float* nu, int32_t n,
+                         int32_t* count_dev, float lr_init, float lr_final, int32_t transition_steps,
+                         float b1, float b2, float eps, float grad_scale, void* stream);
+
 /* ---- accounting for benchmarks: kernels launched by this library, and (between begin/end) CUDA-event
  * time per category {0 render fwd, 1 render bwd, 2 wgrad (SIMT only), 3 heads, 4 misc}.
  * profile_end synchronises the device.  ms_host/scopes_host/launches_host: host arrays of 5.   */

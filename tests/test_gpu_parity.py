@@ -423,3 +423,39 @@ def test_geodesic_inputs_vs_reference_algebra():
     scene_ref = engine.PackedScene(ref['coords'], ref['Omega'], 1.0, ref['g'], ref['dtau'], ref['Sigma'], ref['t_geos'], 0.0,
                                    -1000.0, 8.0, 2.5, 8.0, 4.0, constants.GM_c3(t_units='hr'))
     assert scene.n_active == scene_ref.n_active > 0
+
+
+def test_cuda_graph_replay_of_the_train_step_matches_direct_calls():
+    """gradient_step_image replays a captured [train step -> Adam (device-side counter)] graph; the parameters after
+    several iterations with changing batches must match the direct-call path, and the step counter / learning-rate
+    schedule must advance (also across a counter change made behind the graph's back, as restore_checkpoint does)."""
+    from collections import OrderedDict
+    from bhnerf_b200 import network, optimization, synthetic
+    c = synthetic.make_config('tiny')
+    rt, pr = c['rt'], c['predictor']
+    rta = OrderedDict((k, rt[k]) for k in ('coords', 'Omega', 'J', 'g', 'dtau', 'Sigma', 't_start_obs', 't_geos', 't_injection'))
+    pred = network.NeRF_Predictor(pr['scale'], pr['rmin'], pr['rmax'], pr['z_width'])
+    nt, A, B = len(c['t_frames']), c['A'], c['B']
+    ts = optimization.TrainStep.image(c['t_frames'], c['target'].reshape(nt, A, B), sigma=c['sigma'].reshape(nt, A, B))
+    batches = [np.array([0, 1]), np.array([2, 3]), np.array([1, 3]), np.array([0, 2]), np.array([3, 1])]
+    res = {}
+    for use in (True, False):
+        network._USE_GRAPHS = use
+        try:
+            state = pred.init_state(network.unflatten_params(synthetic.trained_like_flat_params(7)), num_iters=50,
+                                    lr_init=1e-3, lr_final=1e-5)
+            losses = []
+            for i, b in enumerate(batches):
+                if i == 3:
+                    state.step = 20                     # e.g. a restored checkpoint: the schedule must follow
+                loss, state, images = ts(state, rta, b)
+                losses.append(float(loss.item()))
+            res[use] = (state.flat.clone(), losses, int(state.step), images.clone())
+        finally:
+            network._USE_GRAPHS = True
+    (p1, l1, s1, i1), (p0, l0, s0, i0) = res[True], res[False]
+    assert s1 == s0 == 22
+    np.testing.assert_allclose(l1, l0, rtol=1e-5)
+    assert (i1 - i0).abs().max() / i0.abs().max() < 1e-5
+    moved = (p0 - torch.as_tensor(synthetic.trained_like_flat_params(7)).cuda()).abs().max().item()
+    assert moved > 1e-3 and (p1 - p0).abs().max().item() < 2e-3 * moved

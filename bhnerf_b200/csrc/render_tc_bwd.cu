@@ -30,13 +30,6 @@ namespace {
 constexpr int kDThreads = 576;           // 16 epilogue warps + MMA issuer + weight loader
 constexpr int kDMmaWarp = 16;
 constexpr uint32_t DW_BYTES = TC_W_BYTES - 16384u;                 // stages of layers 1..3, contiguous in ws
-// "unit cotangent" plan (U16, one-plane steps): the chain runs on u_l = delta_l / (d loss/d o), which is a product of
-// weights and ReLU masks only -- bounded like the weights, so fp16 (11 significand bits) holds it and the forward's
-// fp16 hi weight planes serve as B.  ONE product per layer instead of two (d_hi*W_hi + d_hi*W_lo with bf16), half the
-// shared memory (104 KB), and the systematic error is the fp16 rounding of W (2^-12) instead of bf16's 2^-9.
-// The epilogue multiplies by d loss/d o in fp32 when it writes the bf16 delta images for the wgrad CTA.
-constexpr uint32_t DW_BYTES_U16 = 32768u + 32768u + 40960u;        // fp16 hi planes of layers 1..3
-__host__ __device__ constexpr uint32_t u16_w_off(int l) { return l == 1 ? 0u : (l == 2 ? 32768u : 65536u); }
 constexpr uint32_t D_SM_W = 0;
 constexpr uint32_t D_SM_W4 = DW_BYTES;                             // 128 floats
 constexpr uint32_t D_SM_BARS = D_SM_W4 + 512;
@@ -80,14 +73,7 @@ tc_dout_kernel(PackedView v, const float* __restrict__ d_images, const float* e,
   }
 }
 
-// masked fp16 pair of the unit cotangents (TMEM operand of the next layer) and masked bf16 pair of the true
-// cotangents u * dout (delta image for the wgrad)
-__device__ __forceinline__ void unit_pack(uint32_t m, float a, float b, float dout, uint32_t& u16, uint32_t& d16) {
-  u16 = pack_f16x2(a, b) & m;
-  d16 = pack_bf16x2(a * dout, b * dout) & m;
-}
-
-template <int PL, bool FUSED, bool U16>
+template <int PL, bool FUSED, bool WIDE>
 __device__ __forceinline__ void
 dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, const PackedView& v,
            const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
@@ -105,7 +91,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 
   if (tid == 0) {
     mbar_init(&bars[DB_WFULL], 1);
-    mbar_init(&bars[DB_AREADY + 0], 8); mbar_init(&bars[DB_AREADY + 1], 8);
+    mbar_init(&bars[DB_AREADY + 0], WIDE ? 16 : 8); mbar_init(&bars[DB_AREADY + 1], WIDE ? 16 : 8);
     mbar_init(&bars[DB_DREADY + 0], 1); mbar_init(&bars[DB_DREADY + 1], 1);
     for (int d = 0; d < kRingDepth; ++d) mbar_init(&bars[DB_GFREE + d], 1);
     *abort_s = 0;
@@ -120,23 +106,17 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
   const uint32_t tbase = *tmem_base_s;
 
   if (warp == kDMmaWarp + 1) {
-    if (lane == 0) {      // resident weights, one shot
-      if (U16) {          // fp16 hi planes of the forward's images, layers 1..3
-        mbar_expect_tx(&bars[DB_WFULL], DW_BYTES_U16);
-        for (int l = 1; l <= 3; ++l)
-          bulk_g2s(wsm + u16_w_off(l), ws + TC_WS_W + tc_stage_off(l), tc_plane_bytes(l), &bars[DB_WFULL]);
-      } else {            // bf16 [hi|lo] images, layers 1..3
-        mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
-        const uint8_t* src = ws + TC_WS_WB + 16384u;
-        bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
-        bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
-        bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
-      }
+    if (lane == 0) {      // resident weights: layers 1..3 [hi|lo] images, one shot
+      mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
+      const uint8_t* src = ws + TC_WS_WB + 16384u;
+      bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
+      bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
+      bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
     }
     __syncwarp();
   } else if (warp == kDMmaWarp) {
     {   // whole warp runs the loop; elect.sync inside the issue wrappers picks the issuing lane
-      const uint32_t idesc = U16 ? make_idesc_f16(128, 128, 0, 0) : make_idesc(128, 128, 0, 0);   // A from TMEM, B K-major
+      const uint32_t idesc = make_idesc(128, 128, 0, 0);      // A from TMEM, B K-major
       uint32_t a_phase[2] = {0u, 0u};
       BH_TIMING_T0 BH_TIMING_DECL(t_wa) BH_TIMING_DECL(t_is)
       bool ok = wait(&bars[DB_WFULL], 0, ab);
@@ -144,7 +124,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         int T0 = (r * ncta + cta) * 2;
         if (T0 >= NT) break;
         for (int l = 3; l >= 1 && ok; --l) {
-          const uint32_t wl = smem_u32(wsm) + (U16 ? u16_w_off(l) : tc_stage_off(l) - 16384u);
+          const uint32_t wl = smem_u32(wsm) + tc_stage_off(l) - 16384u;
           const uint32_t plane = tc_plane_bytes(l), cs = (tc_layer_K(l) / 8u) * 128u;
           for (int s = 0; s < 2; ++s) {
             if (T0 + s >= NT) continue;
@@ -162,7 +142,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
               const uint32_t b_hi = desc_hi(TC_IMG_RS), b_lo0 = desc_lo(wl, cs), b_lo1 = desc_lo(wl + plane, cs);
               const uint32_t kstep = (2u * cs) >> 4;
 #pragma unroll
-              for (int pp = 0; pp < (U16 ? 1 : (PL == 2 ? 3 : 2)); ++pp)
+              for (int pp = 0; pp < (PL == 2 ? 3 : 2); ++pp)
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                   mma_ts_raw(td, ta + (pp == 2 ? 64u : 0u) + (uint32_t)ks * 8u, (pp == 1 ? b_lo1 : b_lo0) + (uint32_t)ks * kstep,
@@ -177,6 +157,183 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       if (lane == 0) { BH_TIMING_STORE(status, 20, t_wa) BH_TIMING_STORE(status, 22, t_is) }
     }
     __syncwarp();
+  } else if (WIDE) {
+    // Epilogue warps: (32-column group, TMEM lane quadrant); thread = one sample row x 32 columns.  ALL 16 warps work on
+    // one tile at a time and alternate between the two slots layer by layer: the epilogue of one tile (half as long as
+    // with 8 warps x 64 columns -- the chain is latency-bound) runs under the MMAs of the other.
+    const int cgrp = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    const int half = cgrp >> 1, cc = cgrp & 1;                  // where these 32 columns sit in the ReLU mask words
+    const uint32_t t_row = tbase + ((uint32_t)(q * 32) << 16);
+    uint32_t d_phase[2] = {0u, 0u};
+    float db4 = 0.f;
+    bool ok = true;
+    const size_t act_fs = tc_acts_bytes_per_frame(v.n_pad, PL), del_fs = tc_delta_bytes_per_frame(v.n_pad, PL);
+    const size_t lstride = (size_t)v.n_pad * 256u, pstride = (size_t)v.n_pad * 1024u;
+    uint32_t pub_addr[2] = {0u, 0u};
+    auto publish_pending = [&](int s) {       // hand a finished tile to the wgrad CTA (one release per warp and tile)
+      if (FUSED && pub_addr[s]) {
+        fence_proxy_async_global();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(pub_addr[s]);
+        pub_addr[s] = 0u;
+      }
+    };
+    // inputs of the next round's two tiles, loaded one round ahead: d loss/d o of the row and its four mask words
+    float dout_next[2] = {0.f, 0.f};
+    uint32_t mk_next[2][4];
+    auto load_inputs = [&](int r) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int T = (r * ncta + cta) * 2 + s;
+        if (T >= NT) continue;
+        const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
+        dout_next[s] = dout_all[(size_t)b * v.n_pad + tile * 128 + row];
+        const uint8_t* mbase = acts + (size_t)b * act_fs + tc_mask_off(v.n_pad, PL);
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          mk_next[s][l] = *reinterpret_cast<const uint32_t*>(mbase + tc_mask_word_off(tile, l, half, row) + cc * 4);
+      }
+    };
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) mk_next[s][l] = 0u;
+    load_inputs(0);
+    BH_TIMING_T0 BH_TIMING_DECL(t_top) BH_TIMING_DECL(t_gf) BH_TIMING_DECL(t_pub) BH_TIMING_DECL(t_wd) BH_TIMING_DECL(t_ep)
+#ifdef BH_TC_TIMING
+    const long long t_loop0 = clock64();
+#endif
+    for (int r = 0; ok; ++r) {
+      const int T0 = (r * ncta + cta) * 2;
+      if (T0 >= NT) break;
+      const bool has[2] = {true, T0 + 1 < NT};
+      float dout[2];
+      uint32_t mk[2][4];
+      uint8_t* del_tile[2];
+      uint32_t rd[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        dout[s] = dout_next[s];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) mk[s][l] = mk_next[s][l];
+      }
+      load_inputs(r + 1);
+      const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
+      // ---- top of both tiles: delta_3[j] = dout * W4[j] * (h3[j] > 0)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (!has[s] || !ok) continue;
+        const int T = T0 + s, b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
+        rd[s] = (uint32_t)(2 * r + s) % kRingDepth;
+        del_tile[s] = FUSED ? link.ring + (size_t)rd[s] * TSET_BYTES : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+        uint8_t* aux = FUSED ? del_tile[s] + 4u * TC_SIMG_BYTES
+                             : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
+        if (FUSED) {       // ring set free: the partner has pulled tile rk - kRingDepth out of it
+          BH_TIMING_BEGIN
+          ok = wait_cluster(&bars[DB_GFREE + rd[s]], (((uint32_t)(2 * r + s) / kRingDepth) & 1u) ^ 1u, ab);
+          BH_TIMING_END(t_gf)
+          if (!ok) break;
+        }
+        BH_TIMING_BEGIN
+        if (cgrp == 0) {
+          db4 += dout[s];
+          const float dh = __bfloat162float(__float2bfloat16_rn(dout[s]));      // aux image: col 0 = hi, col 1 = lo part of dout
+          *reinterpret_cast<uint4*>(aux + sample_img_off(row, 0)) = make_uint4(pack_bf16x2(dh, dout[s] - dh), 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(aux + sample_img_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t d[16], dl[16];
+        const uint32_t mw = mk[s][3];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const uint32_t off = sample_img_off(row, cgrp * 4 + gq);
+          const float* w4 = w4s + (cgrp * 4 + gq) * 8;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), dout[s] * w4[2 * jj], dout[s] * w4[2 * jj + 1], d[4 * gq + jj], dl[4 * gq + jj]);
+          BH_DSTORE(del_tile[s] + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
+          if (PL == 2)
+            *reinterpret_cast<uint4*>(del_tile[s] + pstride + 3 * dls + off) =
+                make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
+        }
+        const uint32_t t_slot = t_row + (uint32_t)s * 256u;
+        tmem_st16(t_slot + 128u + (uint32_t)(cgrp * 16), d);
+        if (PL == 2) tmem_st16(t_slot + 192u + (uint32_t)(cgrp * 16), dl);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
+        BH_TIMING_END(t_top)
+
+      }
+      if (!ok) break;
+      // ---- the chain, alternating between the slots: D = delta_l * W_l^T  ->  delta_{l-1}
+      for (int l = 3; l >= 1 && ok; --l) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (!has[s] || !ok) continue;
+          uint8_t* d_img = del_tile[s] + (size_t)(l - 1) * dls;
+          const uint32_t mw = mk[s][l - 1];
+          const uint32_t t_slot = t_row + (uint32_t)s * 256u;
+          BH_TIMING_BEGIN
+          ok = wait(&bars[DB_DREADY + s], d_phase[s], ab);
+          BH_TIMING_END(t_wd)
+          if (!ok) break;
+          d_phase[s] ^= 1u;
+          tc_fence_after_sync();
+          BH_TIMING_BEGIN
+          uint32_t raw[32];
+          tmem_ld32(t_slot + (uint32_t)(cgrp * 32), raw);
+          tmem_wait_ld();
+          uint32_t d[16], dl[16];
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const uint32_t off = sample_img_off(row, cgrp * 4 + gq);
+            const uint32_t* rr = raw + 8 * gq;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), __uint_as_float(rr[2 * jj]), __uint_as_float(rr[2 * jj + 1]),
+                             d[4 * gq + jj], dl[4 * gq + jj]);
+            BH_DSTORE(d_img + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
+            if (PL == 2)
+              *reinterpret_cast<uint4*>(d_img + pstride + off) = make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
+          }
+          if (l > 1) {
+            tmem_st16(t_slot + 128u + (uint32_t)(cgrp * 16), d);
+            if (PL == 2) tmem_st16(t_slot + 192u + (uint32_t)(cgrp * 16), dl);
+            tmem_wait_st();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
+          }
+          BH_TIMING_END(t_ep)
+        }
+      }
+      if (!ok) break;
+      if (FUSED) {
+        // Hand both tiles over at the end of the round (the proxy fence + release costs ~0.9 k cycles per tile wherever it
+        // is placed).  Measured alternatives, cycles per round: both deferred to the next round's delta_3 as the 8-warp
+        // variant does: 17.2 k with the tensor-core dW4 (the pair serialises: the wgrad CTA idles until the next delta_3
+        // while this CTA waits for ring sets the wgrad CTA has not started on), 13.5 k with the CUDA-core dW4; slot 0
+        // right after its last epilogue: 13.6 k (the release waits for the fresh stores); this placement: 12.9 k.
+        pub_addr[0] = link.peer_bars + rd[0] * 8u;
+        if (has[1]) pub_addr[1] = link.peer_bars + rd[1] * 8u;
+        BH_TIMING_BEGIN
+        publish_pending(0);
+        publish_pending(1);
+        BH_TIMING_END(t_pub)
+      }
+    }
+#ifdef BH_TC_TIMING
+    if (tid == 0) {
+      long long t_loop = clock64() - t_loop0;
+      BH_TIMING_STORE(status, 24, t_top) BH_TIMING_STORE(status, 26, t_gf) BH_TIMING_STORE(status, 28, t_pub)
+      BH_TIMING_STORE(status, 30, t_wd) BH_TIMING_STORE(status, 32, t_ep) BH_TIMING_STORE(status, 34, t_loop)
+    }
+#endif
+    // d b4 = sum dout (network.py:64 bias of the last Dense)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) db4 += __shfl_xor_sync(0xffffffffu, db4, o);
+    if (lane == 0 && db4 != 0.f) atomicAdd(d_params + OFF_B4, db4);
   } else {
     // epilogue warps: (slot, column half, TMEM lane quadrant); thread = one sample row x 64 columns
     const int slot = warp >> 3, half = (warp >> 2) & 1, q = warp & 3, row = q * 32 + lane;
@@ -264,13 +421,6 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
           const uint32_t mw = cc ? mk[3].y : mk[3].x;
           const float* w4 = w4s + (cg0 + 4 * cc + gq) * 8;
-          if (U16) {       // d = unit cotangent W4 .* mask (fp16, chain operand); dl = dout * W4 .* mask (bf16, delta image)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              unit_pack(tc_mask_expand(mw, 4 * gq + jj), w4[2 * jj], w4[2 * jj + 1], dout, d[4 * gq + jj], dl[4 * gq + jj]);
-            BH_DSTORE(del_tile + 3 * dls + off, make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]));
-            continue;
-          }
           delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
           delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
           delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
@@ -313,14 +463,6 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
             const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
             const uint32_t mw = cc ? mkl.y : mkl.x;
             const uint32_t* rr = raw[cc] + 8 * gq;
-            if (U16) {
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                unit_pack(tc_mask_expand(mw, 4 * gq + jj), __uint_as_float(rr[2 * jj]), __uint_as_float(rr[2 * jj + 1]), dout,
-                          d[4 * gq + jj], dl[4 * gq + jj]);
-              BH_DSTORE(d_img + off, make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]));
-              continue;
-            }
             delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), __uint_as_float(rr[0]), __uint_as_float(rr[1]), d[4 * gq + 0], dl[4 * gq + 0]);
             delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), __uint_as_float(rr[2]), __uint_as_float(rr[3]), d[4 * gq + 1], dl[4 * gq + 1]);
             delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), __uint_as_float(rr[4]), __uint_as_float(rr[5]), d[4 * gq + 2], dl[4 * gq + 2]);
@@ -365,14 +507,13 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
   if (tid == 0 && *abort_s) atomicExch(status + 1, 1);
 }
 
-template <int PL, bool U16>
+template <int PL, bool WIDE>
 __global__ void __launch_bounds__(kDThreads, 1)
 tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
                 const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
                 float* __restrict__ d_params, int* __restrict__ status) {
-  static_assert(!(U16 && PL == 2), "the unit-cotangent plan is a one-plane plan");
   extern __shared__ __align__(1024) uint8_t smem[];
-  dgrad_role<PL, false, U16>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, dout_all, Bt, acts,
+  dgrad_role<PL, false, WIDE>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, dout_all, Bt, acts,
                         deltas, d_params, status);
 }
 
@@ -424,7 +565,7 @@ __device__ __forceinline__ int wg_tile(int it, int cta, int ncta, int NT, int& T
   return T < NT ? 1 : 2;
 }
 
-template <int PL, bool FUSED>
+template <int PL, bool FUSED, bool WIDE = false>
 __device__ __forceinline__ void
 wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, int n_pad, int Bt,
            const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas, float* __restrict__ d_params,
@@ -445,7 +586,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
   if (tid == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(&bars[WB_FULL + s], 1); mbar_init(&bars[WB_EMPTY + s], 1); }
     mbar_init(&bars[WB_DONE], 1);
-    for (int s = 0; s < kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], 8);
+    for (int s = 0; s < kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], WIDE ? 16 : 8);
     abort_s[0] = 0; abort_s[1] = 0;
     mbar_fence_init();
   }
@@ -542,17 +683,12 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
           wg_subjob<PL>(idx, j, pa, pb);
           uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
           BH_TIMING_BEGIN
-          ok = wait(&bars[WB_FULL + st], ph, ab);
+          ok = wait(&bars[WB_FULL + st], ph, ab);    // every consumer observes every phase (parity waits cannot skip one)
           BH_TIMING_END(t_fu)
           if (!ok) break;
+          if (j == 4) continue;              // dW4 = h3^T dout runs on the CUDA cores of warps 0-3, which release the stage
           tc_fence_after_sync();
           BH_TIMING_BEGIN
-          // fused: the aux image (job 4) is the last thing pulled out of the ring set -> hand the set back to the
-          // dgrad CTA
-          if (FUSED && j == 4) {
-            if (elect_one()) mbar_arrive_remote(link.peer_bars + ((uint32_t)it % kRingDepth) * 8u);
-            __syncwarp();
-          }
           const uint32_t A = smem_u32(smem + st * W_STAGE_BYTES), B = A + TC_SIMG_BYTES;
           const uint32_t started = later_tile | ((pa | pb) ? 1u : 0u);     // (hi,hi) is each accumulator's first product
           const uint32_t acc_col = j == 0 ? ACC_W3 : j == 1 ? ACC_W2 : j == 2 ? ACC_W1 : j == 3 ? ACC_W0F : ACC_W4;
@@ -582,14 +718,70 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
     }
     __syncwarp();
   } else if (warp < 4 && has_work) {
+    // ===================== dW4 on the CUDA cores =====================
+    // dW4[j] = sum_s h3[s][j] * dout[s] is a 128 x 128 matrix-vector product per tile.  As an MMA (N = 16) it cost a full
+    // SS-form instruction slot per K step -- 8 of the 40 MMAs of a tile, ~20 % of this CTA's issue time, which bounds the
+    // fused pair -- for 16 K MACs.  These four warps idle until the final flush, so they take it: the stage holds the h3
+    // image and the aux image (dout as bf16 hi + lo); thread (column group cg, row phase rp) reads one 16-byte chunk
+    // (8 columns of one row) per row group -- a quarter-warp reads 128 contiguous bytes, no bank conflicts -- and keeps 8
+    // running sums over all tiles of the CTA.
+    bool ok = true;
+    float w4acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w4acc[c] = 0.f;
+    const int rp = lane & 7, cg = warp * 4 + (lane >> 3);       // row phase; column group (8 columns) of this thread
+    {
+      uint32_t cnt = 0;
+      for (int it = 0; ok; ++it) {
+        int T;
+        const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
+        if (tv == 0) break;
+        if (tv == 2) continue;
+        for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
+          int j, pa, pb;
+          wg_subjob<PL>(idx, j, pa, pb);
+          const uint32_t st = cnt % kWStages, ph = (cnt / kWStages) & 1u;
+          ok = wait(&bars[WB_FULL + st], ph, ab);    // observe every phase, consume only job 4
+          if (!ok) break;
+          if (j != 4) continue;
+          // fused: the aux image is the last thing pulled out of the ring set -> hand the set back to the dgrad CTA
+          if (FUSED && tid == 0) mbar_arrive_remote(link.peer_bars + ((uint32_t)it % kRingDepth) * 8u);
+          const uint8_t* img = smem + st * W_STAGE_BYTES + cg * TC_SIMG_CS + rp * 16;
+          const uint8_t* aux = smem + st * W_STAGE_BYTES + TC_SIMG_BYTES + rp * 16;
+#pragma unroll 4
+          for (int rg = 0; rg < 16; ++rg) {
+            const uint32_t dw = *reinterpret_cast<const uint32_t*>(aux + rg * TC_IMG_RS);     // row rg*8+rp: (hi, lo) of dout
+            const float dout = bf16_lo(dw) + bf16_hi(dw);
+            const uint4 hv = *reinterpret_cast<const uint4*>(img + rg * TC_IMG_RS);
+            w4acc[0] = fmaf(bf16_lo(hv.x), dout, w4acc[0]); w4acc[1] = fmaf(bf16_hi(hv.x), dout, w4acc[1]);
+            w4acc[2] = fmaf(bf16_lo(hv.y), dout, w4acc[2]); w4acc[3] = fmaf(bf16_hi(hv.y), dout, w4acc[3]);
+            w4acc[4] = fmaf(bf16_lo(hv.z), dout, w4acc[4]); w4acc[5] = fmaf(bf16_hi(hv.z), dout, w4acc[5]);
+            w4acc[6] = fmaf(bf16_lo(hv.w), dout, w4acc[6]); w4acc[7] = fmaf(bf16_hi(hv.w), dout, w4acc[7]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");      // all four warps are done with the stage
+          if (tid == 0) mbar_arrive(&bars[WB_EMPTY + st]);
+        }
+      }
+    }
+    if (ok) {                                                  // dW4: sum the 8 row phases, one atomic per column
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float vsum = w4acc[c];
+        vsum += __shfl_xor_sync(0xffffffffu, vsum, 1);
+        vsum += __shfl_xor_sync(0xffffffffu, vsum, 2);
+        vsum += __shfl_xor_sync(0xffffffffu, vsum, 4);
+        if (rp == 0 && vsum != 0.f) atomicAdd(d_params + OFF_W4 + cg * 8 + c, vsum);
+        if (rp == 0 && !(fabsf(vsum) <= 3.0e38f)) abort_s[1] = 1;
+      }
+    }
     // ===================== final epilogue: TMEM accumulators -> d_params (atomic accumulate) =====================
-    bool ok = wait(&bars[WB_DONE], 0, ab);
+    ok = ok && wait(&bars[WB_DONE], 0, ab);
     tc_fence_after_sync();
     if (ok) {
       const int n = warp * 32 + lane;
       const uint32_t t_lane = tbase + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < 496; c0 += 16) {
+      for (uint32_t c0 = 0; c0 < ACC_W4; c0 += 16) {
         uint32_t raw[16];
         tmem_ld16(t_lane + c0, raw);
         tmem_wait_ld();
@@ -604,10 +796,9 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
           else if (c < ACC_W1) dst = (c - ACC_B2 == TC_ONES_COL - 16) ? OFF_B2 + n : -1;
           else if (c < ACC_B1) dst = OFF_W1 + (int)(c - ACC_W1) * 128 + n;
           else if (c < ACC_W0F) dst = (c - ACC_B1 == TC_ONES_COL - 16) ? OFF_B1 + n : -1;
-          else if (c < ACC_W4) { int kf = (int)(c - ACC_W0F); dst = kf < BH_NF ? OFF_W0 + kf * 128 + n : (kf == TC_ONES_COL ? OFF_B0 + n : -1); }
-          else dst = (c <= ACC_W4 + 1) ? OFF_W4 + n : -1;       // cols 0,1: h3^T dout_hi + h3^T dout_lo
+          else { int kf = (int)(c - ACC_W0F); dst = kf < BH_NF ? OFF_W0 + kf * 128 + n : (kf == TC_ONES_COL ? OFF_B0 + n : -1); }
           if (dst >= 0 && val != 0.f) atomicAdd(d_params + dst, val);
-          if (dst >= 0 && !(fabsf(val) <= 3.0e38f)) abort_s[1] = 1;     // cotangent overflow (fp16 unit chain): flag it
+          if (dst >= 0 && !(fabsf(val) <= 3.0e38f)) abort_s[1] = 1;     // non-finite gradient (cotangent overflow): flag it
         }
       }
     }
@@ -625,7 +816,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
 tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas,
                 float* __restrict__ d_params, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  wgrad_role<PL, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, n_pad, Bt, acts, deltas, d_params, status);
+  wgrad_role<PL, false, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, n_pad, Bt, acts, deltas, d_params, status);
 }
 
 // =====================================================================================================
@@ -633,7 +824,7 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
 // =====================================================================================================
 constexpr uint32_t F_SM_TOTAL = D_SM_TOTAL > WCfg<1>::SM_TOTAL ? D_SM_TOTAL : WCfg<1>::SM_TOTAL;
 
-template <bool U16>
+template <bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
 tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
                     const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
@@ -645,10 +836,10 @@ tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* _
   link.ring = ring + (size_t)pair * kRingDepth * TSET_BYTES;
   if (rank == 0) {
     link.peer_bars = mapa_u32(smem_u32(smem + WCfg<1>::SM_BARS + WB_GFULL * 8), 1u);
-    dgrad_role<1, true, U16>(smem, pair, npairs, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
+    dgrad_role<1, true, WIDE>(smem, pair, npairs, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
   } else {
     link.peer_bars = mapa_u32(smem_u32(smem + D_SM_BARS + DB_GFREE * 8), 0u);
-    wgrad_role<1, true>(smem, pair, npairs, link, v.n_pad, Bt, acts, nullptr, d_params, status);
+    wgrad_role<1, true, WIDE>(smem, pair, npairs, link, v.n_pad, Bt, acts, nullptr, d_params, status);
   }
 }
 
@@ -662,13 +853,10 @@ int num_sms_b() {
   return g_num_sms_b;
 }
 
-// BHNERF_TC_DGRAD=f16 selects the unit-cotangent fp16 chain.  Measured on B200 (profiles/r1_cycles_bwd_v5.log): it halves
-// the chain's MMA time but the chain is bound by its epilogue latency, not by the tensor pipe -- the extra pack per
-// element makes the backward 10 % SLOWER (3.42 vs 3.09 ms) and the gradient less exact (2.7e-4 vs 1.1e-4), so the
-// two-product bf16 chain stays the default.
-bool dgrad_u16_enabled() {
+// BHNERF_TC_DGRAD_WIDE=0 selects the 8-warps-per-tile dgrad epilogue (A/B measurements)
+bool dgrad_wide_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("BHNERF_TC_DGRAD"); on = (e && e[0] == 'f') ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("BHNERF_TC_DGRAD_WIDE"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
 }
 
@@ -692,7 +880,7 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
   }
   if (PL == 1 && bwd_fused_enabled()) {
     BhProfScope ps(BH_CAT_BWD, 1, st);
-    auto kern = dgrad_u16_enabled() ? tc_bwd_fused_kernel<true> : tc_bwd_fused_kernel<false>;
+    auto kern = dgrad_wide_enabled() ? tc_bwd_fused_kernel<true> : tc_bwd_fused_kernel<false>;
     BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SM_TOTAL));
     int npairs = (NT + 1) / 2; if (npairs > num_sms_b() / 2) npairs = num_sms_b() / 2;
     kern<<<2 * npairs, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts,
@@ -702,7 +890,7 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
   }
   {
     BhProfScope ps(BH_CAT_BWD, 1, st);
-    auto kern = (PL == 1 && dgrad_u16_enabled()) ? tc_dgrad_kernel<PL, PL == 1> : tc_dgrad_kernel<PL, false>;
+    auto kern = dgrad_wide_enabled() ? tc_dgrad_kernel<PL, true> : tc_dgrad_kernel<PL, false>;
     BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SM_TOTAL));
     int grid = (NT + 1) / 2; if (grid > num_sms_b()) grid = num_sms_b();
     kern<<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts, (uint8_t*)delta_ws,

@@ -185,6 +185,10 @@ __device__ __forceinline__ float safe_sin_fast(float a) {      // same float32 A
 #endif
 }
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 // warped + scaled coordinates of one sample (bh_features without the encodings)
 __device__ __forceinline__ bool warp_coords(float x, float y, float z, float om, float tg, float tfc,
                                             const FrameConsts& fc, float* u) {
@@ -218,7 +222,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn_relu(float lo, float hi) {
 }
 
 constexpr uint32_t SM_PART = SM_BARS + 128;                        // [slot][row] partial of the last layer
-constexpr uint32_t SM_TOTAL2 = SM_PART + 2 * 128 * 4;
+// inputs of every thread's NEXT sample (x, y, z, Omega, t_geos, ray, t_frame), staged by cp.async: [slot][half][7][128]
+constexpr uint32_t SM_INBUF = SM_PART + 2 * 128 * 4;
+constexpr uint32_t SM_TOTAL2 = SM_INBUF + 2 * 2 * 7 * 128 * 4;
+static_assert(SM_TOTAL2 <= 232448, "forward shared memory");
 
 // SAVE = bf16 planes of every activation kept for the backward (0, 1, 2).  RANGE = track max|h| per sample: compiled
 // as a second body of the same kernel and entered only when the weight bound of tc_prepare_weights_kernel cannot
@@ -336,15 +343,20 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
     uint32_t d_phase = 0;
     bool ok = true;
     // inputs of the first tile; later tiles are prefetched one round ahead
-    float in_x = 0.f, in_y = 0.f, in_z = 0.f, in_om = 0.f, in_tg = 0.f, in_tf = 0.f;
-    int in_ray = -1;
+    // The next tile's inputs are fetched one round ahead with cp.async into this thread's own shared-memory words (no
+    // barrier: a thread reads back only what it copied).  Holding them in registers instead does not work under the
+    // 96-register cap of this kernel: they were spilled right after the loads, which made the "prefetch" synchronous
+    // (ncu: the top long-scoreboard stalls of the kernel after the barrier spins).
+    float* in_s = reinterpret_cast<float*>(smem + SM_INBUF) + (size_t)((slot * 2 + half) * 7) * 128 + row;
     auto load_inputs = [&](int r) {
       int T = (r * (int)gridDim.x + (int)blockIdx.x) * 2 + slot;
       if (T < NT) {
         const int b = T / tiles_per_frame, i = (T - b * tiles_per_frame) * 128 + row;
-        in_x = v.x[i]; in_y = v.y[i]; in_z = v.z[i]; in_om = v.omega[i]; in_tg = v.tgeo[i];
-        in_tf = t_frames[b]; in_ray = v.ray[i];
+        cp_async4(in_s + 0 * 128, v.x + i); cp_async4(in_s + 1 * 128, v.y + i); cp_async4(in_s + 2 * 128, v.z + i);
+        cp_async4(in_s + 3 * 128, v.omega + i); cp_async4(in_s + 4 * 128, v.tgeo + i); cp_async4(in_s + 5 * 128, v.ray + i);
+        cp_async4(in_s + 6 * 128, t_frames + b);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     load_inputs(0);
     BH_TIMING_T0 BH_TIMING_DECL(t_ft) BH_TIMING_DECL(t_wd) BH_TIMING_DECL(t_ep)
@@ -358,6 +370,10 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
       // ---- warp + posenc in registers: half 0 writes u and the sines (cols 0..11), half 1 the cosines (12..20) ----
       BH_TIMING_BEGIN
       float u[3];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const float in_x = in_s[0 * 128], in_y = in_s[1 * 128], in_z = in_s[2 * 128], in_om = in_s[3 * 128],
+                  in_tg = in_s[4 * 128], in_tf = in_s[6 * 128];
+      const int in_ray = __float_as_int(in_s[5 * 128]);
       const bool valid = warp_coords(in_x, in_y, in_z, in_om, in_tg, bh_frame_time(in_tf, fc), fc, u);
       // the activation bound of tc_prepare_weights_kernel assumes |feature| <= 1; outside it, track the range per sample
       // the weight bound assumes |coords/scale| <= 4 (the reference uses scale = rmax, i.e. <= 1): outside it the range

@@ -194,31 +194,105 @@ class TrainStep(object):
         return self.args[0].t_units
 
 
-def save_checkpoint(checkpoint_dir, state, step, keep=5):
-    """Stand-in for flax.training.checkpoints.save_checkpoint (optimization.py:118-121): same file naming
-    (``checkpoint_<step>``) and ``keep`` policy; payload is a pickled dict of numpy arrays with the flax
-    tree names (msgpack/flax are not installed)."""
+# ---- flax msgpack state format -----------------------------------------------------------------------------------
+# flax.training.checkpoints.save_checkpoint writes flax.serialization.to_bytes(state) = msgpack of the state dict, with
+# every ndarray as ExtType(1, msgpack((shape, dtype.name, raw bytes))) and numpy scalars as ExtType(3, ...)
+# (flax/serialization.py, published format; flax is not installed here, so this restatement is UNPINNED against flax
+# itself -- it is checked against hand-built byte strings of that format in tests/test_abi_host.py).  The state dict of
+# TrainState(params, tx=optax.adam(schedule)) is {'step', 'params', 'opt_state': {'0': {'count','mu','nu'}, '1': {'count'}}}
+# (optax.chain(scale_by_adam, scale_by_schedule), network.py:173-182).
+def _np_to_ext(a):
+    import msgpack
+    a = np.asarray(a)
+    return msgpack.ExtType(1, msgpack.packb((list(a.shape), a.dtype.name, a.tobytes('C')), use_bin_type=True))
+
+
+def _flax_pack(obj):
+    import msgpack
+    if isinstance(obj, dict):
+        return {str(k): _flax_pack(v) for k, v in obj.items()}
+    if isinstance(obj, (np.ndarray, np.generic)):
+        return _np_to_ext(obj)
+    if isinstance(obj, torch.Tensor):
+        return _np_to_ext(obj.detach().cpu().numpy())
+    return obj
+
+
+def _flax_ext_hook(code, data):
+    import msgpack
+    if code == 1:
+        shape, dtype, buf = msgpack.unpackb(data, raw=True)
+        return np.frombuffer(buf, dtype=np.dtype(dtype.decode() if isinstance(dtype, bytes) else dtype)).reshape(shape).copy()
+    if code == 3:
+        dtype, buf = msgpack.unpackb(data, raw=True)
+        return np.frombuffer(buf, dtype=np.dtype(dtype.decode() if isinstance(dtype, bytes) else dtype))[0]
+    if code == 2:
+        re_, im_ = msgpack.unpackb(data)
+        return complex(re_, im_)
+    return msgpack.ExtType(code, data)
+
+
+def state_to_flax_bytes(state):
+    """Bytes of flax.serialization.to_bytes(TrainState) for this state (flat buffers -> flax pytree names)."""
+    import msgpack
+    pred = state.predictor
+    tree = lambda flat: pred._unflatten(flat)
+    d = {'step': int(state.step), 'params': tree(state.flat),
+         'opt_state': {'0': {'count': np.asarray(state.step, dtype=np.int32), 'mu': tree(state.mu), 'nu': tree(state.nu)},
+                       '1': {'count': np.asarray(state.step, dtype=np.int32)}}}
+    return msgpack.packb(_flax_pack(d), use_bin_type=True)
+
+
+def state_from_flax_bytes(state, blob):
+    """Inverse of state_to_flax_bytes; also reads checkpoints written by the reference (flax) itself."""
+    import msgpack
+    d = msgpack.unpackb(blob, ext_hook=_flax_ext_hook, raw=False, strict_map_key=False)
+    pred, dev = state.predictor, state.flat.device
+    state.flat.copy_(torch.as_tensor(pred._flatten(d['params']), device=dev))
+    opt = d.get('opt_state', {})
+    adam = opt.get('0', opt) if isinstance(opt, dict) else {}
+    if 'mu' in adam and 'nu' in adam:
+        state.mu.copy_(torch.as_tensor(pred._flatten(adam['mu']), device=dev))
+        state.nu.copy_(torch.as_tensor(pred._flatten(adam['nu']), device=dev))
+    state.step = int(np.asarray(d.get('step', adam.get('count', 0))))
+    return state
+
+
+def save_checkpoint(checkpoint_dir, state, step, keep=5, fmt=None):
+    """flax.training.checkpoints.save_checkpoint (optimization.py:118-121): file ``checkpoint_<step>`` holding the
+    msgpack state bytes flax writes (``fmt='flax'``, default; ``BHNERF_CHECKPOINT_FORMAT=pickle`` or ``fmt='pickle'`` keeps
+    the earlier pickled dict), same ``keep`` policy."""
+    fmt = fmt or os.environ.get('BHNERF_CHECKPOINT_FORMAT', 'flax')
     os.makedirs(checkpoint_dir, exist_ok=True)
     with open(os.path.join(checkpoint_dir, 'checkpoint_%d' % step), 'wb') as f:
-        pickle.dump(state.state_dict(), f)
+        if fmt == 'pickle':
+            pickle.dump(state.state_dict(), f)
+        else:
+            f.write(state_to_flax_bytes(state))
     ck = sorted([int(n.split('_')[1]) for n in os.listdir(checkpoint_dir) if n.startswith('checkpoint_')])
     for s in ck[:-keep]:
         os.remove(os.path.join(checkpoint_dir, 'checkpoint_%d' % s))
 
 
 def restore_checkpoint(checkpoint_dir, state):
+    """flax.training.checkpoints.restore_checkpoint (network.py:185): latest ``checkpoint_<step>`` of the directory,
+    flax msgpack or the earlier pickle payload (detected by the pickle protocol marker)."""
     if not os.path.isdir(checkpoint_dir):
         return state
-    ck = sorted([int(n.split('_')[1]) for n in os.listdir(checkpoint_dir) if n.startswith('checkpoint_')])
+    ck = sorted([int(n.split('_')[1]) for n in os.listdir(checkpoint_dir)
+                 if n.startswith('checkpoint_') and n.split('_')[1].isdigit()])
     if not ck:
         return state
     with open(os.path.join(checkpoint_dir, 'checkpoint_%d' % ck[-1]), 'rb') as f:
-        d = pickle.load(f)
-    dev = state.flat.device
-    state.flat.copy_(torch.as_tensor(state.predictor._flatten(d["params"]), device=dev))
-    state.mu.copy_(torch.as_tensor(d['mu'], device=dev)); state.nu.copy_(torch.as_tensor(d['nu'], device=dev))
-    state.step = int(d['step'])
-    return state
+        blob = f.read()
+    if blob[:1] == b'\x80':                      # pickle protocol >= 2
+        d = pickle.loads(blob)
+        dev = state.flat.device
+        state.flat.copy_(torch.as_tensor(state.predictor._flatten(d["params"]), device=dev))
+        state.mu.copy_(torch.as_tensor(d['mu'], device=dev)); state.nu.copy_(torch.as_tensor(d['nu'], device=dev))
+        state.step = int(d['step'])
+        return state
+    return state_from_flax_bytes(state, blob)
 
 
 class Optimizer(object):

@@ -128,3 +128,43 @@ def test_frame_sharding_and_pmean_two_gloo_ranks(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_flax_msgpack_checkpoint_format_roundtrip(tmp_path):
+    """optimization.save_checkpoint / restore_checkpoint write and read the msgpack state bytes flax writes
+    (flax.serialization: ndarray = ExtType(1, msgpack((shape, dtype.name, bytes)))).  flax is not installed, so the byte
+    layout is pinned on hand-built strings of that published format, then the state round-trips through a directory."""
+    import msgpack
+    import torch
+    from bhnerf_b200 import network, optimization
+    # known answer: a 2x2 float32 array as flax encodes it
+    a = np.arange(4, dtype=np.float32).reshape(2, 2)
+    want = msgpack.ExtType(1, msgpack.packb(([2, 2], 'float32', a.tobytes()), use_bin_type=True))
+    assert optimization._np_to_ext(a) == want
+    blob = msgpack.packb({'step': 7, 'params': {'w': want}}, use_bin_type=True)
+    back = msgpack.unpackb(blob, ext_hook=optimization._flax_ext_hook, raw=False)
+    assert back['step'] == 7 and np.array_equal(back['params']['w'], a) and back['params']['w'].dtype == np.float32
+    # full state
+    pred = network.NeRF_Predictor(8.0, 2.0, 8.0, 4.0)
+    state = pred.init_state(pred.init_params(seed=3), num_iters=100, lr_init=1e-3, lr_final=1e-5, device='cpu')
+    rng = np.random.default_rng(0)
+    state.mu.copy_(torch.as_tensor(rng.normal(size=state.mu.numel()).astype(np.float32)))
+    state.nu.copy_(torch.as_tensor(rng.uniform(size=state.nu.numel()).astype(np.float32)))
+    state.step = 42
+    tree = msgpack.unpackb(optimization.state_to_flax_bytes(state), ext_hook=optimization._flax_ext_hook, raw=False)
+    assert set(tree) == {'step', 'params', 'opt_state'} and tree['step'] == 42
+    assert tree['params']['MLP_0']['Dense_3']['kernel'].shape == (149, 128)
+    assert set(tree['opt_state']) == {'0', '1'} and set(tree['opt_state']['0']) == {'count', 'mu', 'nu'}
+    assert int(tree['opt_state']['0']['count']) == 42 and tree['opt_state']['0']['nu']['MLP_0']['Dense_4']['bias'].shape == (1,)
+    d = str(tmp_path / 'ck')
+    for step in (10, 20, 30):
+        state.step = step
+        optimization.save_checkpoint(d, state, step, keep=2)
+    assert sorted(os.listdir(d)) == ['checkpoint_20', 'checkpoint_30']
+    fresh = pred.init_state(pred.init_params(seed=9), num_iters=100, lr_init=1e-3, lr_final=1e-5, device='cpu', checkpoint_dir=d)
+    assert fresh.step == 30 and torch.equal(fresh.flat, state.flat) and torch.equal(fresh.mu, state.mu) and torch.equal(fresh.nu, state.nu)
+    # the earlier pickle payload is still readable
+    d2 = str(tmp_path / 'ck2')
+    optimization.save_checkpoint(d2, state, 5, fmt='pickle')
+    old = pred.init_state(pred.init_params(seed=9), num_iters=100, device='cpu', checkpoint_dir=d2)
+    assert torch.equal(old.flat, state.flat) and old.step == 30

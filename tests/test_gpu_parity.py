@@ -277,11 +277,13 @@ def test_size_independent_properties_at_config_shapes(impl):
     assert (grads - g2).abs().max() / g2.abs().max() < 2e-5 and torch.isfinite(grads).all()
 
 
-def test_simt_and_tc_agree_at_config_shape():
+@pytest.mark.parametrize('nt', [8, 1, 3])
+def test_simt_and_tc_agree_at_config_shape(nt):
     """The fp32 SIMT family is the on-device reference for the tcgen05 family at sizes the CPU oracle cannot
-    reach: cfg1 (64x64x64) with 8 frames."""
+    reach: cfg1 (64x64x64, 461 tiles per frame) with 8 frames, and with 1 / 3 frames -- an ODD number of tiles, so the
+    last round of the persistent kernels has one tile (fused backward: one-plane plan of the per-pixel loss)."""
     from bhnerf_b200 import constants, engine, synthetic
-    c = synthetic.make_config('cfg1_tutorial3', nt=8)
+    c = synthetic.make_config('cfg1_tutorial3', nt=nt)
     rt, pr = c['rt'], c['predictor']
     params = torch.as_tensor(synthetic.trained_like_flat_params(7)).cuda()
     scene = engine.PackedScene(rt['coords'], rt['Omega'], rt['J'], rt['g'], rt['dtau'], rt['Sigma'], rt['t_geos'],

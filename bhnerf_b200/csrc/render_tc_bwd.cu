@@ -533,7 +533,7 @@ template <int PL> struct WCfg {
 };
 // WB_GFULL[d]: the four delta images and the aux image of the tile in ring set d are written; 8 remote arrivals
 // (the dgrad CTA's epilogue warps of that slot) per phase
-enum { WB_FULL = 0, WB_EMPTY = 3, WB_DONE = 10, WB_GFULL = 11, WB_NBARS = 11 + kRingDepth };
+enum { WB_FULL = 0, WB_EMPTY = 3, WB_DONE = 10, WB_GFULL = 11, WB_NBARS = 11 + 2 * kRingDepth };   // GFULL[partner][set]
 static_assert(WB_NBARS * 8 + 16 <= 256, "wgrad barrier area");
 // TMEM accumulator columns (lane = n, or j for dW4): [dW3 128 | dW3 skip rows + b3 32] [dW2 128 | b2 16]
 // [dW1 128 | b1 16] [dW0 + b0 32] [dW4 16]
@@ -553,21 +553,25 @@ template <int PL> __device__ __forceinline__ void wg_subjob(int idx, int& j, int
   else { j = 4; pa = idx - 12; pb = 0; }
 }
 
-// Tile order of one wgrad CTA.  Stand-alone: T = cta, cta + ncta, ...   Fused: the tile PAIRS of its dgrad partner,
-// (r * ncta + cta) * 2 + s for s = 0, 1 -- ring sequence number rk = 2r + s, the same numbering the dgrad CTA uses.
-// Returns 0 = done, 1 = tile T valid, 2 = skip (odd tail of the last pair).
-template <bool FUSED>
-__device__ __forceinline__ int wg_tile(int it, int cta, int ncta, int NT, int& T) {
-  if (!FUSED) { T = cta + it * ncta; return T < NT ? 1 : 0; }
-  const int T0 = ((it >> 1) * ncta + cta) * 2;
-  if (T0 >= NT) return 0;
-  T = T0 + (it & 1);
-  return T < NT ? 1 : 2;
+// Tile order of one wgrad CTA.  Stand-alone: T = cta, cta + ncta, ...   Fused: the tile PAIRS of its ND dgrad partners,
+// interleaved partner by partner.  Partner p is dgrad CTA cta*ND + p of ncta*ND; its it_p-th tile is
+// (r * ncta*ND + cta*ND + p) * 2 + s with r = it_p / 2, s = it_p & 1 -- ring sequence number it_p, the numbering that dgrad
+// CTA uses.  Returns 0 = all partners done, 1 = tile valid, 2 = skip (odd tail, or this partner is done already).
+struct WgSeq { int T, p; uint32_t rd, ru; };
+template <bool FUSED, int ND>
+__device__ __forceinline__ int wg_tile(int it, int cta, int ncta, int NT, WgSeq& q) {
+  if (!FUSED) { q.T = cta + it * ncta; q.p = 0; q.rd = 0u; q.ru = 0u; return q.T < NT ? 1 : 0; }
+  const int p = it % ND, itp = it / ND;
+  q.p = p; q.rd = (uint32_t)itp % kRingDepth; q.ru = ((uint32_t)itp / kRingDepth) & 1u;
+  const int T0 = ((itp >> 1) * ncta * ND + cta * ND + p) * 2;
+  if (T0 >= NT) return p == 0 ? 0 : 2;          // partner 0 has the smallest tile numbers: when it is done, all are
+  q.T = T0 + (itp & 1);
+  return q.T < NT ? 1 : 2;
 }
 
-template <int PL, bool FUSED, bool WIDE = false>
+template <int PL, bool FUSED, bool WIDE = false, int ND = 1>
 __device__ __forceinline__ void
-wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, int n_pad, int Bt,
+wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, int n_pad, int Bt,
            const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas, float* __restrict__ d_params,
            int* __restrict__ status) {
   static_assert(!(FUSED && PL == 2), "the fused pair runs the one-plane plan");
@@ -586,7 +590,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
   if (tid == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(&bars[WB_FULL + s], 1); mbar_init(&bars[WB_EMPTY + s], 1); }
     mbar_init(&bars[WB_DONE], 1);
-    for (int s = 0; s < kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], WIDE ? 16 : 8);
+    for (int s = 0; s < ND * kRingDepth; ++s) mbar_init(&bars[WB_GFULL + s], WIDE ? 16 : 8);
     abort_s[0] = 0; abort_s[1] = 0;
     mbar_fence_init();
   }
@@ -596,8 +600,8 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
   if (FUSED) cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tbase = *tmem_base_s;
-  int T_first;
-  const bool has_work = wg_tile<FUSED>(0, cta, ncta, NT, T_first) == 1;
+  WgSeq q_first;
+  const bool has_work = wg_tile<FUSED, ND>(0, cta, ncta, NT, q_first) == 1;
 
   if (warp == 5) {
     // ===================== producer: bulk copies of the saved images =====================
@@ -606,23 +610,24 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
       bool ok = true;
       BH_TIMING_T0 BH_TIMING_DECL(t_gfl) BH_TIMING_DECL(t_em)
       for (int it = 0; ok; ++it) {
-        int T;
-        const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
+        WgSeq sq;
+        const int tv = wg_tile<FUSED, ND>(it, cta, ncta, NT, sq);
         if (tv == 0) break;
         if (tv == 2) continue;
+        const int T = sq.T;
         const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
         const uint8_t* act_tile = acts + (size_t)b * act_fs + (size_t)tile * TC_SIMG_BYTES;
         const uint8_t* feat_tile = acts + (size_t)b * act_fs + pstride * PL + (size_t)tile * TC_FIMG_BYTES;
-        // fused: ring set rd; use number ru of that set selects the barrier phase
-        const uint32_t rd = (uint32_t)it % kRingDepth, ru = ((uint32_t)it / kRingDepth) & 1u;
-        const uint8_t* del_tile = FUSED ? link.ring + (size_t)rd * TSET_BYTES
+        // fused: ring set rd of partner p; use number ru of that set selects the barrier phase
+        const uint32_t rd = sq.rd, ru = sq.ru;
+        const uint8_t* del_tile = FUSED ? links[sq.p].ring + (size_t)rd * TSET_BYTES
                                         : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
         const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;
         const uint8_t* aux_src = FUSED ? del_tile + 4u * TC_SIMG_BYTES
                                        : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
         if (FUSED) {      // the dgrad CTA has written this tile's delta / aux images into ring set rd
           BH_TIMING_BEGIN
-          ok = wait_cluster(&bars[WB_GFULL + rd], ru, ab);
+          ok = wait_cluster(&bars[WB_GFULL + sq.p * kRingDepth + rd], ru, ab);
           BH_TIMING_END(t_gfl)
           if (!ok) break;
           fence_proxy_async_global();
@@ -674,8 +679,8 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
 #endif
       // all operands are [s][c] images read MN-major: K (= sample) groups advance by RS, M/N groups by CS
       for (int it = 0; ok; ++it) {
-        int T;
-        const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
+        WgSeq sq;
+        const int tv = wg_tile<FUSED, ND>(it, cta, ncta, NT, sq);
         if (tv == 0) break;
         if (tv == 2) continue;
         for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
@@ -733,8 +738,8 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
     {
       uint32_t cnt = 0;
       for (int it = 0; ok; ++it) {
-        int T;
-        const int tv = wg_tile<FUSED>(it, cta, ncta, NT, T);
+        WgSeq sq;
+        const int tv = wg_tile<FUSED, ND>(it, cta, ncta, NT, sq);
         if (tv == 0) break;
         if (tv == 2) continue;
         for (int idx = 0; idx < wg_num_subjobs<PL>() && ok; ++idx, ++cnt) {
@@ -745,7 +750,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, in
           if (!ok) break;
           if (j != 4) continue;
           // fused: the aux image is the last thing pulled out of the ring set -> hand the set back to the dgrad CTA
-          if (FUSED && tid == 0) mbar_arrive_remote(link.peer_bars + ((uint32_t)it % kRingDepth) * 8u);
+          if (FUSED && tid == 0) mbar_arrive_remote(links[sq.p].peer_bars + sq.rd * 8u);
           const uint8_t* img = smem + st * W_STAGE_BYTES + cg * TC_SIMG_CS + rp * 16;
           const uint8_t* aux = smem + st * W_STAGE_BYTES + TC_SIMG_BYTES + rp * 16;
 #pragma unroll 4
@@ -816,7 +821,8 @@ __global__ void __launch_bounds__(kWThreads, 1)
 tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas,
                 float* __restrict__ d_params, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  wgrad_role<PL, false, false>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, n_pad, Bt, acts, deltas, d_params, status);
+  const PairLink none{nullptr, 0u};
+  wgrad_role<PL, false, false, 1>(smem, (int)blockIdx.x, (int)gridDim.x, &none, n_pad, Bt, acts, deltas, d_params, status);
 }
 
 // =====================================================================================================
@@ -824,22 +830,29 @@ tc_wgrad_kernel(int n_pad, int Bt, const uint8_t* __restrict__ acts, const uint8
 // =====================================================================================================
 constexpr uint32_t F_SM_TOTAL = D_SM_TOTAL > WCfg<1>::SM_TOTAL ? D_SM_TOTAL : WCfg<1>::SM_TOTAL;
 
-template <bool WIDE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
+// ND dgrad CTAs (cluster ranks 0..ND-1) feed ONE wgrad CTA (rank ND).  ND = 1 is the production shape (74 pairs, all
+// resident); ND = 2 is kept as a measured alternative (see bwd_dgrad_per_cluster).
+template <bool WIDE, int ND>
+__global__ void __cluster_dims__(ND + 1, 1, 1) __launch_bounds__(kDThreads, 1)
 tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
                     const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
                     float* __restrict__ d_params, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t rank = cluster_ctarank();
-  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
-  PairLink link;
-  link.ring = ring + (size_t)pair * kRingDepth * TSET_BYTES;
-  if (rank == 0) {
-    link.peer_bars = mapa_u32(smem_u32(smem + WCfg<1>::SM_BARS + WB_GFULL * 8), 1u);
-    dgrad_role<1, true, WIDE>(smem, pair, npairs, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
+  const int cl = (int)(blockIdx.x / (ND + 1)), ncl = (int)(gridDim.x / (ND + 1));
+  if (rank < (uint32_t)ND) {
+    PairLink link;
+    link.ring = ring + (size_t)(cl * ND + (int)rank) * kRingDepth * TSET_BYTES;
+    link.peer_bars = mapa_u32(smem_u32(smem + WCfg<1>::SM_BARS + (WB_GFULL + rank * kRingDepth) * 8), (uint32_t)ND);
+    dgrad_role<1, true, WIDE>(smem, cl * ND + (int)rank, ncl * ND, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
   } else {
-    link.peer_bars = mapa_u32(smem_u32(smem + D_SM_BARS + DB_GFREE * 8), 0u);
-    wgrad_role<1, true, WIDE>(smem, pair, npairs, link, v.n_pad, Bt, acts, nullptr, d_params, status);
+    PairLink links[ND];
+#pragma unroll
+    for (int p = 0; p < ND; ++p) {
+      links[p].ring = ring + (size_t)(cl * ND + p) * kRingDepth * TSET_BYTES;
+      links[p].peer_bars = mapa_u32(smem_u32(smem + D_SM_BARS + DB_GFREE * 8), (uint32_t)p);
+    }
+    wgrad_role<1, true, WIDE, ND>(smem, cl, ncl, links, v.n_pad, Bt, acts, nullptr, d_params, status);
   }
 }
 
@@ -858,6 +871,16 @@ bool dgrad_wide_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("BHNERF_TC_DGRAD_WIDE"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
+}
+
+// dgrad CTAs per wgrad CTA in the fused backward (BHNERF_TC_BWD_ND=1|2, default 1).  Measured on B200 (cfg2 x 25 frames):
+// clusters of 3 are parity-green but SLOWER, 4.35 ms against 2.80 ms -- only 45 of them are resident at once (135 of 148
+// SMs) and one wgrad CTA cannot feed on two rings: its stage ring stalls behind the CUDA-core dW4 and the dgrad CTAs wait
+// 10 k cycles per round for free ring sets.
+int bwd_dgrad_per_cluster() {
+  static int nd = 0;
+  if (nd == 0) { const char* e = getenv("BHNERF_TC_BWD_ND"); nd = (e && e[0] == '2') ? 2 : 1; }
+  return nd;
 }
 
 bool bwd_fused_enabled() {                 // BHNERF_TC_FUSED=0 selects the two-kernel backward (A/B measurements)
@@ -880,11 +903,29 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
   }
   if (PL == 1 && bwd_fused_enabled()) {
     BhProfScope ps(BH_CAT_BWD, 1, st);
-    auto kern = dgrad_wide_enabled() ? tc_bwd_fused_kernel<true> : tc_bwd_fused_kernel<false>;
+    const int nd = bwd_dgrad_per_cluster();
+    auto kern = !dgrad_wide_enabled() ? tc_bwd_fused_kernel<false, 1>
+                                      : (nd == 2 ? tc_bwd_fused_kernel<true, 2> : tc_bwd_fused_kernel<true, 1>);
     BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SM_TOTAL));
-    int npairs = (NT + 1) / 2; if (npairs > num_sms_b() / 2) npairs = num_sms_b() / 2;
-    kern<<<2 * npairs, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts,
-                                                    (uint8_t*)delta_ws, d_params, status);
+    const int ndc = dgrad_wide_enabled() ? nd : 1;
+    int ncl = ((NT + 1) / 2 + ndc - 1) / ndc; if (ncl > num_sms_b() / (ndc + 1)) ncl = num_sms_b() / (ndc + 1);
+    // a cluster lives inside one GPC: launch no more clusters than can be resident at once (persistent kernel, a second
+    // wave would double its time)
+    static int max_cl[3] = {0, 0, 0};
+    if (max_cl[ndc] == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((ndc + 1) * (num_sms_b() / (ndc + 1))); cfg.blockDim = dim3(kDThreads); cfg.dynamicSmemBytes = F_SM_TOTAL;
+      cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = ndc + 1; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms_b() / (ndc + 1); }
+      max_cl[ndc] = n;
+      if (getenv("BHNERF_DEBUG")) fprintf(stderr, "bhnerf_b200: fused backward, clusters of %d: %d resident at once\n", ndc + 1, n);
+    }
+    if (ncl > max_cl[ndc]) ncl = max_cl[ndc];
+    kern<<<(ndc + 1) * ncl, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts,
+                                                         (uint8_t*)delta_ws, d_params, status);
     BH_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -916,7 +957,7 @@ size_t bh_tc_delta_bytes_per_frame(int n_pad, int planes) {
   return (planes == 1 && bwd_fused_enabled()) ? 0 : tc_delta_bytes_per_frame(n_pad, planes);
 }
 size_t bh_tc_delta_fixed_bytes(int planes) {
-  return (planes == 1 && bwd_fused_enabled()) ? (size_t)(num_sms_b() / 2) * kRingDepth * TSET_BYTES : 0;
+  return (planes == 1 && bwd_fused_enabled()) ? (size_t)(2 * (num_sms_b() / 3) + 2) * kRingDepth * TSET_BYTES : 0;   // >= dgrad CTAs of either cluster shape
 }
 
 int bh_tc_bwd(const PackedView& v, const void* ws, const float* params, const float* d_images, int Bt,

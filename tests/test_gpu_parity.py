@@ -461,3 +461,40 @@ def test_cuda_graph_replay_of_the_train_step_matches_direct_calls():
     assert (i1 - i0).abs().max() / i0.abs().max() < 1e-5
     moved = (p0 - torch.as_tensor(synthetic.trained_like_flat_params(7)).cuda()).abs().max().item()
     assert moved > 1e-3 and (p1 - p0).abs().max().item() < 2e-3 * moved
+
+
+def test_optimizer_run_fits_a_synthetic_movie_and_resumes_from_a_flax_checkpoint(tmp_path):
+    """The reference's whole loop through its own API (optimization.Optimizer.run -> TrainStep -> gradient_step_image):
+    a NeRF is fitted to the movie another (trained-like) NeRF renders; the movie loss must drop, checkpoints are written
+    in flax's msgpack format with the reference's keep policy, and a new Optimizer resumes from the latest one."""
+    from collections import OrderedDict
+    from bhnerf_b200 import network, optimization, synthetic
+    c = synthetic.make_config('tiny')
+    rt, pr = c['rt'], c['predictor']
+    rta = OrderedDict((k, rt[k]) for k in ('coords', 'Omega', 'J', 'g', 'dtau', 'Sigma', 't_start_obs', 't_geos', 't_injection'))
+    pred = network.NeRF_Predictor(pr['scale'], pr['rmin'], pr['rmax'], pr['z_width'])
+    truth = network.unflatten_params(synthetic.trained_like_flat_params(7))
+    movie = network.image_plane_prediction(truth, pred.apply, c['t_frames'], *rta.values(), 'hr').cpu().numpy()
+    assert movie.shape == (4, c['A'], c['B']) and movie.max() > 0
+    ts = optimization.TrainStep.image(c['t_frames'], movie, sigma=1.0, dtype='full')
+    ck = str(tmp_path / 'run')
+    np.random.seed(1)
+    opt = optimization.Optimizer({'num_iters': 60, 'lr_init': 2e-3, 'lr_final': 1e-4, 'seed': 1}, pred, rta, save_period=20,
+                                 checkpoint_dir=ck, keep=2)
+    loss0 = optimization.total_movie_loss(2, opt.state, ts, rta)
+    seen = []
+    opt.run(2, ts, rta, log_fns=[optimization.LogFn(lambda o: seen.append(float(o.loss.item())), log_period=10)])
+    loss1 = optimization.total_movie_loss(2, opt.state, ts, rta)
+    assert opt.state.step == 60 and len(seen) == 7 and np.isfinite(seen).all()
+    assert loss1 < 0.5 * loss0, (loss0, loss1)
+    files = sorted(os.listdir(ck))
+    assert 'NeRF_Predictor_params.yml' in files and [f for f in files if f.startswith('checkpoint_')] == ['checkpoint_40', 'checkpoint_60']
+    import msgpack
+    tree = msgpack.unpackb(open(os.path.join(ck, 'checkpoint_60'), 'rb').read(), ext_hook=optimization._flax_ext_hook, raw=False)
+    assert tree['step'] == 60 and tree['params']['MLP_0']['Dense_0']['kernel'].shape == (21, 128)
+    opt2 = optimization.Optimizer({'num_iters': 10, 'lr_init': 2e-3, 'lr_final': 1e-4, 'seed': 5}, pred, rta, checkpoint_dir=ck)
+    assert opt2.state.step == 60 and torch.equal(opt2.state.flat, opt.state.flat) and torch.equal(opt2.state.nu, opt.state.nu)
+    opt2.run(2, ts, rta)
+    assert opt2.state.step == 70 and optimization.total_movie_loss(2, opt2.state, ts, rta) < loss0
+    restored = network.NeRF_Predictor.from_yml(ck)
+    assert restored.domain() == pred.domain()

@@ -592,7 +592,7 @@ size_t bh_tc_acts_bytes_per_frame(int n_pad, int planes) { return tc_acts_bytes_
 
 // Precision plan of the backward: the saved activations / cotangents are bf16.  With the hi plane
 // only, the rounding noise of the wgrad reduction averages out as 1/sqrt(#sample-frames) (measured 1e-4 of the
-// gradient at 4.5e6 sample-frames); below 2^19 sample-frames per step both planes are kept (x3 products, error
+// gradient at 4.5e6 sample-frames); below 2^20 sample-frames per step both planes are kept (x3 products, error
 // ~1e-5 at any size).  BHNERF_TC_PLANES=1|2 overrides.
 // Per-pixel image loss ('full'): every pixel's residual enters the gradient with its own sign-stable weight, there is
 // no cancellation between rays, and the one-plane noise is 3.0e-4 of the gradient already at 1.1e4 sample-frames
@@ -613,7 +613,8 @@ int bh_tc_planes(int n_active, int Bt_total) {
     forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
   }
   if (forced) return forced;
-  return ((long long)n_active * (long long)Bt_total < (1ll << 19)) ? 2 : 1;
+  // 2^20: the worst measured case (Q/U lightcurve golden, 6.0e-3 at 1.1e4 sample-frames) scales to 6e-4 there
+  return ((long long)n_active * (long long)Bt_total < (1ll << 20)) ? 2 : 1;
 }
 size_t bh_tc_ws_bytes() { return 1u << 20; }
 

@@ -527,7 +527,7 @@ constexpr int kWThreads = 192;             // warps 0-3 final epilogue, warp 4 M
 // appended to the big ones (N = 160 / 144) instead of being issued on their own.
 constexpr uint32_t W_STAGE_BYTES = 2u * TC_SIMG_BYTES + TC_FIMG_BYTES;
 template <int PL> struct WCfg {
-  static constexpr int kWStages = PL == 2 ? 2 : 3;                            // the two-plane plan is for small steps
+  static constexpr int kWStages = 3;
   static constexpr uint32_t SM_BARS = kWStages * W_STAGE_BYTES;
   static constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 };

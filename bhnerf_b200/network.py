@@ -592,3 +592,20 @@ def sample_3d_grid(apply_fn, params, t_frame=0, t_start_obs=0, Omega=0, fov=None
         raise AttributeError('Either coords or fov+resolution must be provided')
     t_units = getattr(t_frame, 'unit', None)
     return apply_fn({'params': params}, t_frame, t_units, coords, Omega, t_start_obs, 0.0, 0.0)
+
+
+def image_plane_checkpoint(raytracing_args, checkpoint_dir, t, rmin=0.0, rmax=np.inf, batchsize=20):
+    """bhnerf/network.py:896-906: load the predictor + latest checkpoint of a run and render the whole movie (forward
+    only, chunked).  Returns a numpy array (nt, [S,] A, B)."""
+    from . import optimization
+    predictor = NeRF_Predictor.from_yml(checkpoint_dir)
+    predictor.rmax = min(rmax, predictor.rmax)
+    predictor.rmin = max(rmin, predictor.rmin)
+    params = predictor.init_params(raytracing_args)
+    state = predictor.init_state(params, checkpoint_dir=checkpoint_dir)
+    J = np.atleast_1d(raytracing_args)[0]['J']
+    num_stokes = 1 if np.isscalar(J) else np.shape(J)[0]
+    target = np.zeros((len(t), num_stokes)) if not np.isscalar(J) else np.zeros((len(t), 1))
+    train_step = optimization.TrainStep.image(t, target, dtype='lc')
+    _, image_plane = optimization.total_movie_loss(batchsize, state, train_step, raytracing_args, return_frames=True)
+    return image_plane

@@ -498,3 +498,19 @@ def test_optimizer_run_fits_a_synthetic_movie_and_resumes_from_a_flax_checkpoint
     assert opt2.state.step == 70 and optimization.total_movie_loss(2, opt2.state, ts, rta) < loss0
     restored = network.NeRF_Predictor.from_yml(ck)
     assert restored.domain() == pred.domain()
+    # forward-only model selection on the finished run (network.image_plane_checkpoint, alma.chi2_lightcurves / chi2_df)
+    from bhnerf_b200 import alma
+    frames = network.image_plane_checkpoint(rta, ck, c['t_frames'], batchsize=2)
+    direct = network.image_plane_prediction(opt2.state.params, pred.apply, c['t_frames'], *rta.values(), 'hr').cpu().numpy()
+    assert frames.shape == direct.shape and np.abs(frames - direct).max() <= 1e-6 * np.abs(direct).max()
+    lc = movie.sum(axis=(-1, -2))                                # unpolarized: data (nt,), as image_plane.sum((-1,-2))
+    chi2 = alma.chi2_lightcurves(rta, ck, c['t_frames'], lc, sigma=0.5)
+    want = float(np.sum(((direct.sum(axis=(-1, -2)) - lc) / 0.5) ** 2) / 4)
+    assert abs(chi2 - want) <= 1e-4 * max(want, 1e-12)
+    df = alma.chi2_df([30.0, 60.0], 0.2, [0, 1], {}, str(tmp_path) + '/{}_{}', c['t_frames'], lc, sigma=0.5,
+                      raytracing_args_fn=lambda inc, spin: rta, final_step=70)
+    assert df.shape == (2, 2) and df.isna().all().all()          # no run directories of that pattern: all NaN, as the reference
+    os.rename(ck, str(tmp_path) + '/60.0_1')
+    df = alma.chi2_df([30.0, 60.0], 0.2, [0, 1], {}, str(tmp_path) + '/{}_{}', c['t_frames'], lc, sigma=0.5,
+                      raytracing_args_fn=lambda inc, spin: rta, final_step=70)
+    assert abs(df.loc[60.0, 'seed 1'] - want) <= 1e-4 * max(want, 1e-12) and df.isna().sum().sum() == 3

@@ -51,6 +51,7 @@ SIGNATURES = {
     'bhnerf_profile_begin': (C.c_int, []),
     'bhnerf_profile_end': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'bhnerf_grid_render_fwd': (C.c_int, [_SP, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    'bhnerf_interpolate_coords': (C.c_int, [_vp, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _vp, C.c_int64, _vp, _vp]),
     'bhnerf_grid_render_bwd': (C.c_int, [_SP, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp]),
     'bhnerf_geodesic_inputs': (C.c_int, [_vp] * 7 + [C.c_int64, _i32, C.c_double, C.c_double, C.c_double, C.c_double]
                                + [_vp] * 7),

@@ -136,6 +136,20 @@ grid_render_bwd_kernel(PackedView v, FrameConsts fc, GridDesc gd, const float* _
   }
 }
 
+// emission.interpolate_coords (bhnerf/emission.py:213-232) as a stand-alone stage: coords [N,3] (world units, last axis
+// x,y,z as velocity_warp_coords returns them) -> trilinear lookup; NaN coordinates give 0 (mode 0: scipy 'constant').
+template <int MODE>
+__global__ void __launch_bounds__(256)
+interpolate_coords_kernel(GridDesc gd, const float* __restrict__ coords, long long N, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    float ic[3];
+    ic[0] = (coords[3 * i + 0] + 0.5f * gd.fx) / gd.fx * (float)(gd.nx - 1);
+    ic[1] = (coords[3 * i + 1] + 0.5f * gd.fy) / gd.fy * (float)(gd.ny - 1);
+    ic[2] = (coords[3 * i + 2] + 0.5f * gd.fz) / gd.fz * (float)(gd.nz - 1);
+    out[i] = trilinear<MODE>(ic, gd);
+  }
+}
+
 int check_grid_args(const bhnerf_scene_t* sc, const float* grid, int nx, int ny, int nz, float fx, float fy, float fz,
                     const float* t_frames, int Bt) {
   BH_REQUIRE(sc && sc->packed, "grid_render: scene is NULL / not prepacked");
@@ -162,6 +176,21 @@ extern "C" int bhnerf_grid_render_fwd(const bhnerf_scene_t* sc, const float* gri
   int blocks = (int)((warps + 7) / 8); if (blocks > 148 * 64) blocks = 148 * 64;
   if (mode == 0) grid_render_fwd_kernel<0><<<blocks, 256, 0, st>>>(v, fc, gd, t_frames, Bt, images, e_out);
   else grid_render_fwd_kernel<1><<<blocks, 256, 0, st>>>(v, fc, gd, t_frames, Bt, images, e_out);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bhnerf_interpolate_coords(const float* grid, int32_t nx, int32_t ny, int32_t nz, float fov_x, float fov_y,
+                                         float fov_z, int32_t mode, const float* coords, int64_t N, float* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_REQUIRE(grid && coords && out && N > 0, "interpolate_coords: NULL argument or N <= 0");
+  BH_REQUIRE(nx >= 2 && ny >= 2 && nz >= 2 && fov_x > 0.f && fov_y > 0.f && fov_z > 0.f, "interpolate_coords: bad grid");
+  BH_REQUIRE(mode == 0 || mode == 1, "interpolate_coords: unknown mode %d", mode);
+  GridDesc gd{grid, nx, ny, nz, fov_x, fov_y, fov_z};
+  BhProfScope ps(BH_CAT_MISC, 1, st);
+  int blocks = (int)((N + 255) / 256); if (blocks > 148 * 32) blocks = 148 * 32;
+  if (mode == 0) interpolate_coords_kernel<0><<<blocks, 256, 0, st>>>(gd, coords, (long long)N, out);
+  else interpolate_coords_kernel<1><<<blocks, 256, 0, st>>>(gd, coords, (long long)N, out);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

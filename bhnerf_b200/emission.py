@@ -113,3 +113,22 @@ def image_plane_dynamics(emission_0, geos, Omega, t_frames, t_injection, J=1.0, 
     if np.ndim(utils.time_value(t_frames, t_units or 'hr')) == 0:
         out = out[0] if e0.ndim == 3 else out[:, 0]
     return out
+
+
+def interpolate_coords(emission, coords, fov=None):
+    """bhnerf/emission.py:213-232 on the GPU (C ABI: bhnerf_interpolate_coords): trilinear lookup of a 3D emission grid at
+    world coordinates ``coords`` (..., 3) -- the layout velocity_warp_coords returns -- with scipy's order-1 / cval=0 rule.
+    ``fov`` as in image_plane_dynamics for grids without xarray coordinates.  Returns a device tensor of shape coords[:-1]."""
+    lib = _lib.load()
+    dev = torch.device('cuda')
+    fx, fy, fz = _grid_fov(emission, fov)
+    grid = engine._dev_f32(np.asarray(emission, dtype=np.float32) if not isinstance(emission, torch.Tensor) else emission, dev)
+    assert grid.dim() == 3, 'emission must be a 3D grid'
+    c = engine._dev_f32(coords, dev)
+    assert c.shape[-1] == 3, 'coords must have x,y,z on the last axis'
+    shape = tuple(c.shape[:-1])
+    c = c.reshape(-1, 3).contiguous()
+    out = torch.empty(c.shape[0], dtype=torch.float32, device=dev)
+    check(lib.bhnerf_interpolate_coords(engine._ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2], fx, fy, fz, 0,
+                                        engine._ptr(c), c.shape[0], engine._ptr(out), engine._stream()))
+    return out.reshape(shape)

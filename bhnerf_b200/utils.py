@@ -28,3 +28,9 @@ def time_value(t, t_units='hr'):
     if hasattr(t, 'to') and hasattr(t, 'unit'):
         return np.asarray(t.to(t_units).value, dtype=np.float64)
     return np.asarray(t, dtype=np.float64)
+
+
+def world_to_image_coords(coords, fov, npix, use_jax=False):
+    """bhnerf/utils.py:160-166: (coords + fov/2) / fov * (npix - 1) per axis (last axis of coords)."""
+    coords = np.asarray(coords)
+    return np.stack([(coords[..., i] + fov[i] / 2.0) / fov[i] * (npix[i] - 1) for i in range(coords.shape[-1])], axis=-1)

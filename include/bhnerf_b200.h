@@ -158,6 +158,11 @@ int bhnerf_radiative_transfer(const float* emission, const float* g, const float
 int bhnerf_grid_render_fwd(const bhnerf_scene_t* scene, const float* grid, int32_t nx, int32_t ny,
                            int32_t nz, float fov_x, float fov_y, float fov_z, int32_t mode,
                            const float* t_frames, int32_t Bt, float* images, float* e_out, void* stream);
+/* stand-alone lookup: emission.interpolate_coords (bhnerf/emission.py:213-232; mode 0 = scipy rule, 1 = jax rule).
+ * coords [N,3] world units (x,y,z innermost, the layout velocity_warp_coords returns), out [N]; NaN coordinates -> 0. */
+int bhnerf_interpolate_coords(const float* grid, int32_t nx, int32_t ny, int32_t nz, float fov_x,
+                              float fov_y, float fov_z, int32_t mode, const float* coords, int64_t N,
+                              float* out, void* stream);
 int bhnerf_grid_render_bwd(const bhnerf_scene_t* scene, const float* grid, int32_t nx, int32_t ny,
                            int32_t nz, float fov_x, float fov_y, float fov_z, const float* t_frames,
                            int32_t Bt, const float* d_images, float* d_grid, void* stream);

@@ -350,6 +350,16 @@ def test_image_plane_dynamics_vs_reference_and_oracle():
                                         t_units='hr').cpu().numpy()
     assert abs(constants.GM_c3(t_units='hr') - float(d['GM_c3'])) < 1e-9
     assert rel(out, d['images_early']) < IMG_TOL and (out[0] == 0).all(), rel(out, d['images_early'])
+    # the stand-alone stages compose to the same thing: velocity_warp_coords -> interpolate_coords -> radiative_trasfer
+    from bhnerf_b200 import kgeo
+    warped = emission.velocity_warp_coords(geo['coords'], geo['Omega'], tfM, 0.0, geo['t_geos'], float(d['t_injection']))
+    e = emission.interpolate_coords(d['emission_0'], warped, fov=fov)
+    import scipy.ndimage
+    ic = np.moveaxis((warped.cpu().numpy().astype(np.float64) + fov / 2) / fov * (d['emission_0'].shape[0] - 1), -1, 0)
+    e_ref = scipy.ndimage.map_coordinates(d['emission_0'].astype(np.float64), ic, order=1, cval=0.0)
+    assert e.shape == e_ref.shape and np.abs(e.cpu().numpy() - e_ref).max() < 2e-4 * np.abs(e_ref).max()
+    staged = kgeo.radiative_trasfer(e, geo['g'], geo['dtau'], geo['Sigma']).cpu().numpy()
+    assert rel(staged, d['images_g']) < 5e-4
     # a movie of grids: (T, nt, A, B) as in the reference
     mov = np.stack([d['emission_0'], 2.0 * d['emission_0']])
     out = emission.image_plane_dynamics(mov, _geo_ns(geo), geo['Omega'], tfM, float(d['t_injection']), t_start_obs=0.0,

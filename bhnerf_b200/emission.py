@@ -23,8 +23,8 @@ def velocity_warp_coords(coords, Omega, t_frames, t_start_obs, t_geos, t_injecti
     pts = tuple(coords.shape[1:])
     N = int(np.prod(pts))
     c = coords.reshape(3, N).contiguous()
-    Om = engine._dev_f32(Omega, dev); Om = (Om.expand(pts) if Om.dim() == 0 else Om).reshape(N).contiguous()
-    tg = engine._dev_f32(t_geos, dev); tg = (tg.expand(pts) if tg.dim() == 0 else tg).reshape(N).contiguous()
+    Om = engine._dev_f32(Omega, dev); Om = (Om.reshape(()).expand(pts) if Om.numel() == 1 else Om).reshape(N).contiguous()
+    tg = engine._dev_f32(t_geos, dev); tg = (tg.reshape(()).expand(pts) if tg.numel() == 1 else tg).reshape(N).contiguous()
     scalar_t = np.ndim(t_frames) == 0 and not isinstance(t_frames, torch.Tensor)
     tf = engine._dev_f32(np.atleast_1d(utils.time_value(t_frames, t_units or 'hr')), dev)
     out = torch.empty((tf.numel(), N, 3), dtype=torch.float32, device=dev)
@@ -132,3 +132,32 @@ def interpolate_coords(emission, coords, fov=None):
     check(lib.bhnerf_interpolate_coords(engine._ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2], fx, fy, fz, 0,
                                         engine._ptr(c), c.shape[0], engine._ptr(out), engine._stream()))
     return out.reshape(shape)
+
+
+def propogate_flatspace_emission(emission_0, Omega_3D, t_frames, t_start_obs=None, rot_axis=[0, 0, 1],
+                                 M=constants.sgra_mass, fov=None, t_units=None):
+    """bhnerf/emission.py:305-341 (sic): the 3D movie of an initial emission grid sheared by the velocity field in flat
+    space -- the two GPU stages velocity_warp_coords (t_geos = t_injection = 0) and interpolate_coords on the grid's own
+    voxel centres.  Returns a device tensor (nt, nx, ny, nz)."""
+    e0 = np.asarray(emission_0, dtype=np.float32)
+    fx, fy, fz = _grid_fov(emission_0, fov)
+    axes = [np.linspace(-f / 2, f / 2, n, dtype=np.float32) for f, n in zip((fx, fy, fz), e0.shape)]
+    x, y, z = np.meshgrid(*axes, indexing='ij')
+    if t_start_obs is None:
+        t_start_obs = t_frames[0] if np.ndim(t_frames) else t_frames
+    warped = velocity_warp_coords([x, y, z], Omega_3D, t_frames, t_start_obs, 0.0, 0.0, rot_axis=rot_axis, M=M, t_units=t_units)
+    return interpolate_coords(e0, warped, fov=(fx, fy, fz))
+
+
+def rotate_evpa(stokes, angle, axis=0):
+    """bhnerf/emission.py:395-407: rotate the linear-polarization pair (Q, U) of a Stokes stack by ``angle`` (EVPA rotates
+    by the angle, Q + iU by twice it); stacks of 2 (Q,U), 3 (I,Q,U) or 4 (I,Q,U,V) components along ``axis``."""
+    stokes = np.asarray(stokes)
+    n = stokes.shape[axis]
+    if n not in (2, 3, 4):
+        raise AttributeError('Shape of stokes vector along axis={} not supported'.format(axis))
+    iq = 0 if n == 2 else 1
+    comps = [np.take(stokes, k, axis) for k in range(n)]
+    p = np.exp(2j * angle) * (comps[iq] + 1j * comps[iq + 1])
+    comps[iq], comps[iq + 1] = p.real, p.imag
+    return np.stack(comps, axis=axis)

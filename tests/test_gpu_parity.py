@@ -360,6 +360,17 @@ def test_image_plane_dynamics_vs_reference_and_oracle():
     assert e.shape == e_ref.shape and np.abs(e.cpu().numpy() - e_ref).max() < 2e-4 * np.abs(e_ref).max()
     staged = kgeo.radiative_trasfer(e, geo['g'], geo['dtau'], geo['Sigma']).cpu().numpy()
     assert rel(staged, d['images_g']) < 5e-4
+    # flat-space propagation of the grid itself (propogate_flatspace_emission): identity at t = t_start, finite and
+    # mass-preserving to a few per cent later (a rigid-ish shear of a compact blob well inside the grid)
+    ax = np.linspace(-fov / 2, fov / 2, d['emission_0'].shape[0])
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing='ij')
+    Om3 = 1.0 / (np.maximum(np.sqrt(X ** 2 + Y ** 2 + Z ** 2), 2.0) ** 1.5)
+    blob = np.exp(-((X - 3.0) ** 2 + Y ** 2 + Z ** 2) / 2.0).astype(np.float32)
+    mov3 = emission.propogate_flatspace_emission(blob, Om3, np.array([0.0, 20.0]), fov=fov).cpu().numpy()
+    assert mov3.shape == (2,) + blob.shape and np.abs(mov3[0] - blob).max() < 1e-5
+    assert abs(mov3[1].sum() / blob.sum() - 1.0) < 0.05 and np.abs(mov3[1] - blob).max() > 0.1
+    qu = emission.rotate_evpa(np.stack([np.ones(3), np.zeros(3)]), np.pi / 4)
+    assert np.allclose(qu, [[0, 0, 0], [1, 1, 1]], atol=1e-12)
     # a movie of grids: (T, nt, A, B) as in the reference
     mov = np.stack([d['emission_0'], 2.0 * d['emission_0']])
     out = emission.image_plane_dynamics(mov, _geo_ns(geo), geo['Omega'], tfM, float(d['t_injection']), t_start_obs=0.0,

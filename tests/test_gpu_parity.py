@@ -535,3 +535,48 @@ def test_optimizer_run_fits_a_synthetic_movie_and_resumes_from_a_flax_checkpoint
     df = alma.chi2_df([30.0, 60.0], 0.2, [0, 1], {}, str(tmp_path) + '/{}_{}', c['t_frames'], lc, sigma=0.5,
                       raytracing_args_fn=lambda inc, spin: rta, final_step=70)
     assert abs(df.loc[60.0, 'seed 1'] - want) <= 1e-4 * max(want, 1e-12) and df.isna().sum().sum() == 3
+
+
+def test_reference_call_patterns_of_the_standalone_stages():
+    """Argument shapes the reference's callers use: scalar frame time (no frame axis in the result), scalar Omega /
+    t_geos (sample_3d_grid passes 0), coords as (3, N), emission with leading (frame, Stokes) axes, single-frame polarized
+    prediction (jnp.squeeze semantics of network.py:418)."""
+    from bhnerf_b200 import emission, kgeo, network
+    from oracle import bhnerf_oracle as O
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    d = np.load(os.path.join(G, 'ref_stages.npz'))
+    c = float(d['GM_c3'])
+    co = geo['coords']
+    t0, tinj = float(d['t_start_obs']), float(d['t_injection'])
+    # scalar frame time, hours with t_units -> (16,16,32,3); compare with the batched call's slice
+    w1 = emission.velocity_warp_coords(co, geo['Omega'], 0.5, t0, geo['t_geos'], tinj, t_units='hr').cpu().numpy()
+    wb = emission.velocity_warp_coords(co, geo['Omega'], np.array([0.13, 0.5]), t0, geo['t_geos'], tinj, t_units='hr').cpu().numpy()
+    assert w1.shape == co.shape[1:] + (3,) and wb.shape == (2,) + co.shape[1:] + (3,)
+    assert np.array_equal(np.nan_to_num(w1), np.nan_to_num(wb[1]))
+    ref = O.velocity_warp_coords(co, geo['Omega'], np.array([0.5]), t0, geo['t_geos'], tinj, c, torch.float64).numpy()[0]
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(w1), ok) and np.abs(w1[ok] - ref[ok]).max() < 2e-3      # fp32 theta at t_M ~ 1e3
+    # scalar Omega and t_geos on a flat (3, N) point list
+    pts = co.reshape(3, -1)[:, :500]
+    w2 = emission.velocity_warp_coords(pts, 0.05, np.array([0.0, 0.2]), 0.0, 0.0, 0.0, t_units='hr').cpu().numpy()
+    ref2 = O.velocity_warp_coords(pts, np.float64(0.05), np.array([0.0, 0.2]), 0.0, np.float64(0.0), 0.0, c, torch.float64).numpy()
+    assert w2.shape == (2, 500, 3) and np.abs(w2 - ref2).max() < 1e-4 * np.abs(ref2).max()
+    # radiative transfer with leading (frame, Stokes) axes
+    rng = np.random.default_rng(2)
+    e = rng.uniform(size=(3, 2) + co.shape[1:]).astype(np.float32)
+    rtv = kgeo.radiative_trasfer(e, geo['g'], geo['dtau'], geo['Sigma']).cpu().numpy()
+    want = (geo['g'].astype(np.float64) ** 2 * e * geo['dtau'] * geo['Sigma']).sum(-1)
+    assert rtv.shape == (3, 2, 16, 16) and np.abs(rtv - want).max() < 1e-5 * np.abs(want).max()
+    # fill with the default arguments (only z_width = 2 bites) and an explicit fill value
+    f = emission.fill_unsupervised_emission(e, co, fill_value=-1.0).cpu().numpy()
+    outside = np.abs(co[2]) > 2.0
+    assert (f[..., outside] == -1).all() and np.array_equal(f[..., ~outside], e[..., ~outside])
+    # single polarized frame: (S, A, B) after the squeeze
+    pred = network.NeRF_Predictor(8.0, 2.5, 8.0, 4.0)
+    params = pred.init_params(seed=2)
+    J = np.stack([np.ones_like(geo['g']), 0.5 * np.ones_like(geo['g'])])
+    rta = network.raytracing_args(_geo_ns(geo), geo['Omega'], tinj, t0, J=J)
+    img = network.image_plane_prediction(params, pred.apply, np.array([0.7]), *rta.values(), 'hr')
+    assert tuple(img.shape) == (2, 16, 16) and torch.allclose(img[1], 0.5 * img[0], rtol=1e-5, atol=0)
+    e3 = pred.apply({'params': params}, 0.7, 'hr', pts, 0.0, t0, 0.0, 0.0)
+    assert e3.shape == (500,) and np.isfinite(e3).all()

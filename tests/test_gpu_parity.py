@@ -580,3 +580,37 @@ def test_reference_call_patterns_of_the_standalone_stages():
     assert tuple(img.shape) == (2, 16, 16) and torch.allclose(img[1], 0.5 * img[0], rtol=1e-5, atol=0)
     e3 = pred.apply({'params': params}, 0.7, 'hr', pts, 0.0, t0, 0.0, 0.0)
     assert e3.shape == (500,) and np.isfinite(e3).all()
+
+
+def test_multi_loss_train_step_image_plus_visibilities():
+    """TrainStep.__add__ (optimization.py:181-187): an image loss and a visibility loss in one iteration = two sequential
+    gradient steps on the same state, the second one at the parameters the first one produced.  Both updates against the
+    oracle (value_and_grad + optax Adam restated), the second gradient evaluated live at the oracle's updated parameters."""
+    from collections import OrderedDict
+    from bhnerf_b200 import network, optimization
+    from oracle import bhnerf_oracle as O
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    d1 = np.load(os.path.join(G, 'case_image_full.npz'))
+    d2 = np.load(os.path.join(G, 'case_vis.npz'))
+    assert np.array_equal(d1['params_flat'], d2['params_flat']) and np.array_equal(d1['t_frames'], d2['t_frames'])
+    prd = dict(scale=float(d1['scale']), rmin=float(d1['rmin']), rmax=float(d1['rmax']), z_width=float(d1['z_width']))
+    pred = network.NeRF_Predictor(prd['scale'], prd['rmin'], prd['rmax'], prd['z_width'])
+    rt = OrderedDict(coords=geo['coords'], Omega=geo['Omega'], J=1.0, g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
+                     t_start_obs=float(d1['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d1['t_injection']))
+    ts = optimization.TrainStep.image(d1['t_frames'], d1['target'], sigma=1.0, dtype='full') + optimization.TrainStep.eht(
+        d2['t_frames'], d2['target'], d2['sigma'], d2['A'], dtype='vis', scale=1.0)
+    assert ts.num_losses == 2
+    state = pred.init_state(network.unflatten_params(d1['params_flat']), num_iters=100, lr_init=1e-3, lr_final=1e-5)
+    loss, state, images = ts(state, rt, np.arange(4))
+    assert state.step == 2
+    # oracle: step 1 at params0 (golden gradient), step 2 at the updated parameters
+    p0 = d1['params_flat'].astype(np.float64)
+    z = np.zeros(55169)
+    p1, mu, nu = O.adam_step(p0, d1['grads'], z, z, 0, 1e-3, 1e-5, 100)
+    out2 = O.value_and_grad(O.unflatten_params(p1.astype(np.float32)), 'eht', 'vis', d2['target'], d2['sigma'], d2['A'],
+                            d2['t_frames'], dict(rt), prd)
+    p2, _, _ = O.adam_step(p1.astype(np.float32).astype(np.float64), out2['grads'], mu, nu, 1, 1e-3, 1e-5, 100)
+    assert abs(loss.item() - (float(d1['loss']) + out2['loss'])) / (float(d1['loss']) + out2['loss']) < 2 * IMG_TOL
+    got = state.flat.cpu().numpy().astype(np.float64)
+    upd_err = np.abs((got - p0) - (p2 - p0)).max() / 2e-3            # two steps of ~lr each
+    assert upd_err < 3e-2, upd_err

@@ -614,3 +614,18 @@ def test_multi_loss_train_step_image_plus_visibilities():
     got = state.flat.cpu().numpy().astype(np.float64)
     upd_err = np.abs((got - p0) - (p2 - p0)).max() / 2e-3            # two steps of ~lr each
     assert upd_err < 3e-2, upd_err
+
+
+def test_two_rank_nccl_step_matches_oracle():
+    """Frame-sharded step on 2 GPUs (NCCL all-reduce mean + Adam) against the oracle; needs a 2-GPU box (skipped otherwise;
+    last run recorded in profiles/r1_multirank_check_v6.log)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29547', os.path.join(root, 'scripts', 'multirank_check.py')],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('ranks identical: True') == 2

@@ -170,12 +170,17 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
     const size_t act_fs = tc_acts_bytes_per_frame(v.n_pad, PL), del_fs = tc_delta_bytes_per_frame(v.n_pad, PL);
     const size_t lstride = (size_t)v.n_pad * 256u, pstride = (size_t)v.n_pad * 1024u;
     uint32_t pub_addr[2] = {0u, 0u};
-    auto publish_pending = [&](int s) {       // hand a finished tile to the wgrad CTA (one release per warp and tile)
-      if (FUSED && pub_addr[s]) {
+    // hand the finished tiles to the wgrad CTA: ONE proxy fence per warp covers the stores of both tiles of the round,
+    // then one release per tile
+    auto publish_both = [&]() {
+      if (FUSED && (pub_addr[0] | pub_addr[1])) {
         fence_proxy_async_global();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(pub_addr[s]);
-        pub_addr[s] = 0u;
+        if (lane == 0) {
+          if (pub_addr[0]) mbar_arrive_remote(pub_addr[0]);
+          if (pub_addr[1]) mbar_arrive_remote(pub_addr[1]);
+        }
+        pub_addr[0] = 0u; pub_addr[1] = 0u;
       }
     };
     // inputs of the next round's two tiles, loaded one round ahead: d loss/d o of the row and its four mask words
@@ -318,8 +323,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         pub_addr[0] = link.peer_bars + rd[0] * 8u;
         if (has[1]) pub_addr[1] = link.peer_bars + rd[1] * 8u;
         BH_TIMING_BEGIN
-        publish_pending(0);
-        publish_pending(1);
+        publish_both();
         BH_TIMING_END(t_pub)
       }
     }

@@ -5,7 +5,8 @@
                   [--workload cfg2_lp_flare] [--frames F]
 
 One "step" = one fused fwd+bwd train step (render -> loss -> parameter gradient [-> all-reduce-mean -> Adam in
-the e2e leg]) over ALL frames of the workload.  Default workload = BASELINE.json configs[1]
+the e2e leg, where network.gradient_step_image replays the captured CUDA graph of the step at N=1]) over ALL frames
+of the workload.  Default workload = BASELINE.json configs[1]
 (128x128 rays x 128 samples x 100 frames, Q/U lightcurve loss), which fits one GPU.  With N ranks every rank
 renders its own 100 frames (weak scaling: global batch = 100*N frames) and the ranks exchange the 220 KB
 gradient with one NCCL all-reduce per step, as the reference's pmap/pmean does (network.py:620).

@@ -37,7 +37,7 @@ def parse():
     ap.add_argument('--kernels', default=os.environ.get('BHNERF_IMPL', 'auto'))
     ap.add_argument('--workload', default='cfg2_lp_flare')
     ap.add_argument('--frames', type=int, default=None, help='override the number of frames (debug)')
-    ap.add_argument('--max-workspace-gb', type=float, default=24.0)
+    ap.add_argument('--max-workspace-gb', type=float, default=40.0)
     ap.add_argument('--cpu-frames', type=int, default=None, help='frames in the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()

@@ -182,6 +182,7 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
                      (e_saved && acts_saved ? 0 : (size_t)sc->n_pad * 4);
   int Bc = per_frame ? (int)(avail / per_frame) : Bt;
   if (Bc > Bt) Bc = Bt;
+  if (Bc >= 1) { const int nchunks = (Bt + Bc - 1) / Bc; Bc = (Bt + nchunks - 1) / nchunks; }   // equal chunks
   BH_REQUIRE(Bc >= 1, "render_bwd: workspace (%zu B) cannot hold one frame (%zu B + %zu B fixed)",
              workspace_bytes, per_frame, fixed);
   BH_CHECK_CUDA(cudaMemsetAsync(d_params, 0, BHNERF_N_PARAMS * sizeof(float), st));
@@ -255,6 +256,7 @@ extern "C" int bhnerf_train_step_image(const bhnerf_scene_t* sc, const float* pa
              workspace_bytes, fixed + per_frame);
   int Bc = (int)((workspace_bytes - fixed) / per_frame);
   if (Bc > Bt) Bc = Bt;
+  { const int nchunks = (Bt + Bc - 1) / Bc; Bc = (Bt + nchunks - 1) / nchunks; }      // equal chunks instead of a short tail
   BH_CHECK_CUDA(cudaMemsetAsync(d_params, 0, BHNERF_N_PARAMS * sizeof(float), st));
   BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   if (impl == BHNERF_IMPL_TC) { if (int r = bh_tc_prepare_weights(params, ws, st)) return r; }

@@ -28,7 +28,8 @@ def resolve_impl(impl=None):
 
 DEFAULT_IMPL = IMPL_TC     # tcgen05 family (parity-green on B200); 'simt' selects the fp32 reference kernels
 # cap on the activation workspace of one fused step / backward; more frames than fit are processed in chunks
-DEFAULT_MAX_WORKSPACE = int(float(os.environ.get('BHNERF_MAX_WORKSPACE_GB', '16')) * 2 ** 30)
+# default 40 GB of the B200's 180 GB: a full cfg2 step (100 frames x 0.33 GB of saved activations) runs as one chunk
+DEFAULT_MAX_WORKSPACE = int(float(os.environ.get('BHNERF_MAX_WORKSPACE_GB', '40')) * 2 ** 30)
 
 
 def _ptr(t):

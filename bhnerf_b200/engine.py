@@ -342,7 +342,9 @@ def frames_per_chunk(scene, Bt, impl=None, max_workspace=None):
     lib = _lib.load(); impl = resolve_impl(impl)
     per = max(lib.bhnerf_acts_bytes(scene.ref, 1, impl), 1)
     cap = DEFAULT_MAX_WORKSPACE if max_workspace is None else int(max_workspace)
-    return int(max(1, min(Bt, cap // per)))
+    bc = int(max(1, min(Bt, cap // per)))
+    nchunks = (Bt + bc - 1) // bc
+    return (Bt + nchunks - 1) // nchunks          # equal chunks instead of a short tail
 
 
 def adam_step(params, grads, mu, nu, count, lr_init=1e-4, lr_final=1e-6, num_iters=5000, b1=0.9, b2=0.999,

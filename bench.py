@@ -135,7 +135,7 @@ def run_reference(args):
         v, dt, cores = cpu_reference_leg(args.workload, nfr)
         vals.append(v); secs.append(dt)
     v = float(np.mean(vals))
-    line = {'metric': 'geodesic samples/s, fwd+bwd train step', 'value': v, 'unit': 'dense samples/s', 'n_gpus': 0,
+    line = {'metric': 'geodesic samples/s, fwd+bwd train step', 'value': v, 'unit': 'dense samples/s', 'n_gpus': args.gpus,
             'impl': 'reference', 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean(secs)),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload, 'rays': c['n'] * c['n'], 'samples_per_ray': c['G'], 'frames': c['nt'],

@@ -82,12 +82,17 @@ extern "C" int64_t bhnerf_launch_count(void) {
   return (int64_t)t;
 }
 
-extern "C" int bhnerf_workspace_status(const void* workspace, int32_t* flags_host, void* stream) {
+extern "C" int bhnerf_workspace_status(void* workspace, int32_t* flags_host, void* stream) {
   BH_REQUIRE(workspace && flags_host, "workspace_status: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  BH_CHECK_CUDA(cudaMemcpyAsync(flags_host, workspace, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  // words [55] magic | [56..64) sticky flags (tc_common.cuh): read, then cleared, so a flag raised by ANY step since the
+  // previous call is reported exactly once
+  int32_t w[9];
+  BH_CHECK_CUDA(cudaMemcpyAsync(w, (const char*)workspace + 55 * sizeof(int32_t), sizeof(w), cudaMemcpyDeviceToHost, st));
   BH_CHECK_CUDA(cudaStreamSynchronize(st));
-  for (int i = 5; i < 8; ++i) flags_host[i] = 0;        // words past the flags hold optional cycle counters
+  const bool used = w[0] == 0x62683230;                 // a workspace no tcgen05 step has touched yet reports all-clear
+  for (int i = 0; i < 8; ++i) flags_host[i] = (used && i < 5) ? w[1 + i] : 0;
+  if (used) BH_CHECK_CUDA(cudaMemsetAsync((char*)workspace + 56 * sizeof(int32_t), 0, 8 * sizeof(int32_t), st));
   return 0;
 }
 
@@ -178,8 +183,11 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
   BH_REQUIRE(workspace_bytes >= fixed, "render_bwd: workspace too small");
   char* p = ws + fixed;
   size_t avail = workspace_bytes - fixed;
-  size_t per_frame = bwd_frame_bytes(sc, impl, pl) + (acts_saved ? 0 : acts_bytes_per_frame(sc, impl, pl)) +
-                     (e_saved && acts_saved ? 0 : (size_t)sc->n_pad * 4);
+  // the forward is recomputed unless BOTH residuals were passed in; the recompute carves activations AND e out of the
+  // workspace, so both are counted whenever it runs (a mixed call used to overrun a capped workspace)
+  const bool recompute = (acts_saved == nullptr) || (e_saved == nullptr);
+  size_t per_frame = bwd_frame_bytes(sc, impl, pl) +
+                     (recompute ? acts_bytes_per_frame(sc, impl, pl) + (size_t)sc->n_pad * 4 : 0);
   int Bc = per_frame ? (int)(avail / per_frame) : Bt;
   if (Bc > Bt) Bc = Bt;
   if (Bc >= 1) { const int nchunks = (Bt + Bc - 1) / Bc; Bc = (Bt + nchunks - 1) / nchunks; }   // equal chunks
@@ -187,7 +195,6 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
              workspace_bytes, per_frame, fixed);
   BH_CHECK_CUDA(cudaMemsetAsync(d_params, 0, BHNERF_N_PARAMS * sizeof(float), st));
   if (impl == BHNERF_IMPL_TC) { if (int r = bh_tc_prepare_weights(params, ws, st)) return r; }
-  bool recompute = (acts_saved == nullptr) || (e_saved == nullptr);
   for (int b0 = 0; b0 < Bt; b0 += Bc) {
     int nb = (Bt - b0 < Bc) ? Bt - b0 : Bc;
     char* q = p;
@@ -197,7 +204,8 @@ extern "C" int bhnerf_render_bwd(const bhnerf_scene_t* sc, const float* params, 
     const float* e = e_saved ? e_saved + (size_t)b0 * sc->n_pad : nullptr;
     if (recompute) {
       void* acts_ws = q; q += acts_bytes_per_frame(sc, impl, pl) * nb;
-      float* e_ws = (float*)q;
+      float* e_ws = (float*)q; q += (size_t)sc->n_pad * 4 * nb;
+      BH_REQUIRE((size_t)(q - ws) <= workspace_bytes, "render_bwd: internal workspace accounting error");
       if (impl == BHNERF_IMPL_SIMT) {
         if (int r = bh_simt_fwd(v, fc, params, t_frames + b0, nb, e_ws, (float*)acts_ws, st)) return r;
       } else {

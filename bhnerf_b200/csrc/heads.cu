@@ -270,11 +270,17 @@ extern "C" int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, in
 // ---------------------------------------------------------------------------------------------
 // optax.adam + polynomial_schedule(power=1) (network.py:173-174, :621)
 // ---------------------------------------------------------------------------------------------
+// `guard` (or NULL): the five health flags of the step that produced `g` (first words of the tcgen05 workspace).  If any
+// is set the update is skipped -- a gradient from an overflowed / aborted step is never applied; the sticky copy of the
+// flags makes the caller's next bhnerf_workspace_status poll raise.
+__device__ __forceinline__ bool adam_guard_tripped(const int* guard) {
+  return guard && (guard[0] | guard[1] | guard[2] | guard[3] | guard[4]);
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
                             float* __restrict__ nu, int n, float lr, float b1, float b2, float eps,
-                            float bc1, float bc2, float gscale) {
+                            float bc1, float bc2, float gscale, const int* __restrict__ guard) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || adam_guard_tripped(guard)) return;
   float gi = g[i] * gscale;
   float m = b1 * mu[i] + (1.f - b1) * gi;
   float v = b2 * nu[i] + (1.f - b2) * gi * gi;
@@ -285,7 +291,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 extern "C" int bhnerf_adam_step(float* params, const float* grads, float* mu, float* nu, int32_t n,
                                 int32_t count, float lr_init, float lr_final, int32_t transition_steps,
-                                float b1, float b2, float eps, float grad_scale, void* stream) {
+                                float b1, float b2, float eps, float grad_scale, const int32_t* guard, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BH_REQUIRE(transition_steps > 0, "adam: transition_steps must be > 0");
   int c = count < 0 ? 0 : (count > transition_steps ? transition_steps : count);
@@ -294,7 +300,7 @@ extern "C" int bhnerf_adam_step(float* params, const float* grads, float* mu, fl
   double t = (double)count + 1.0;
   float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
   BhProfScope ps(BH_CAT_MISC, 1, st);
-  adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(params, grads, mu, nu, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(params, grads, mu, nu, n, lr, b1, b2, eps, bc1, bc2, grad_scale, guard);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -304,7 +310,8 @@ extern "C" int bhnerf_adam_step(float* params, const float* grads, float* mu, fl
 // *count_dev inside the kernel (double precision, one thread per block), and a second one-thread kernel advances it.
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
                                 float* __restrict__ nu, int n, const int* __restrict__ count_dev, float lr_init,
-                                float lr_final, int transition_steps, float b1, float b2, float eps, float gscale) {
+                                float lr_final, int transition_steps, float b1, float b2, float eps, float gscale,
+                                const int* __restrict__ guard) {
   __shared__ float sh[3];
   if (threadIdx.x == 0) {
     const int count = *count_dev;
@@ -318,7 +325,7 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   __syncthreads();
   const float lr = sh[0], bc1 = sh[1], bc2 = sh[2];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || adam_guard_tripped(guard)) return;
   float gi = g[i] * gscale;
   float m = b1 * mu[i] + (1.f - b1) * gi;
   float v = b2 * nu[i] + (1.f - b2) * gi * gi;
@@ -330,12 +337,13 @@ __global__ void counter_inc_kernel(int* c) { *c += 1; }
 
 extern "C" int bhnerf_adam_step_dev(float* params, const float* grads, float* mu, float* nu, int32_t n,
                                     int32_t* count_dev, float lr_init, float lr_final, int32_t transition_steps,
-                                    float b1, float b2, float eps, float grad_scale, void* stream) {
+                                    float b1, float b2, float eps, float grad_scale, const int32_t* guard,
+                                    void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BH_REQUIRE(transition_steps > 0 && count_dev, "adam_dev: transition_steps must be > 0 and count_dev non-NULL");
   BhProfScope ps(BH_CAT_MISC, 2, st);
   adam_dev_kernel<<<(n + 255) / 256, 256, 0, st>>>(params, grads, mu, nu, n, count_dev, lr_init, lr_final, transition_steps,
-                                                   b1, b2, eps, grad_scale);
+                                                   b1, b2, eps, grad_scale, guard);
   counter_inc_kernel<<<1, 1, 0, st>>>(count_dev);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -46,7 +46,18 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ params, uint
       c[TC_C_W4 + idx] = params[OFF_W4 + idx];
     }
     if (idx == 0) c[TC_C_B4] = params[OFF_B4];
-    if (idx < 64) ((int*)(ws + TC_WS_STATUS))[idx] = 0;
+    // per-step flags and cycle counters are reset; the sticky flags [56..64) survive until bhnerf_workspace_status reads
+    // them (a workspace seen for the first time -- no magic word -- has them zeroed once)
+    {
+      int* stw = (int*)(ws + TC_WS_STATUS);
+      if (blockIdx.x == 0) {
+        if (idx < TC_STATUS_MAGIC_WORD) stw[idx] = 0;
+        if (idx == 0 && stw[TC_STATUS_MAGIC_WORD] != TC_STATUS_MAGIC) {
+          for (int k = 0; k < 8; ++k) stw[TC_STATUS_STICKY + k] = 0;
+          stw[TC_STATUS_MAGIC_WORD] = TC_STATUS_MAGIC;
+        }
+      }
+    }
     if (blockIdx.x == 0) {
       // Can a hidden activation leave the fp16 operand range?  With |coords/scale| <= 4 and |sin| <= 1:
       //   B_0 = max_n sum_k f_k |W0[k][n]| + |b0[n]| (f_k = 4 for k < 3, else 1),
@@ -219,6 +230,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn_relu(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+// residual of the fp16 hi plane, x - float(hi), for both halves of a packed pair: ONE full-rate FMA-pipe instruction per
+// element (fma.rn.f32.f16 = FHFMA: hi * -1 + x, exact -- the residual has <= 13 significant bits).  The earlier form, a
+// mantissa mask (LOP3) + FADD per element, ran on the ALU pipe, which binds this epilogue: F2FP, LOP3, PRMT and HSET2 all
+// issue there at one warp-instruction per 2 cycles (profiles/r2_epi_probe.log).
+__device__ __forceinline__ void f16x2_residual(uint32_t hi, float x0, float x1, float& r0, float& r1) {
+  asm("{\n\t.reg .b16 l, u, m;\n\tmov.b32 {l, u}, %2;\n\tmov.b16 m, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, l, m, %3;\n\tfma.rn.f32.f16 %1, u, m, %4;\n\t}"
+      : "=f"(r0), "=f"(r1) : "r"(hi), "f"(x0), "f"(x1));
 }
 
 constexpr uint32_t SM_PART = SM_BARS + 128;                        // [slot][row] partial of the last layer
@@ -479,12 +500,18 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               hi[j] = pack_f16x2_rz_relu(x[2 * j], x[2 * j + 1]);
-              // lo = x - hi: hi is x rounded toward zero to 11 significant bits, i.e. x with the low 13 mantissa bits
-              // cleared (for x <= 0 the relu-conversion gives 0 either way; below the fp16 normal range the two differ
-              // by < 2^-24 absolute).  A mask instead of two f16->f32 conversions: the conversion pipe is what binds
-              // this epilogue (fwd 3.09 -> 2.78 ms on cfg2 x 25 frames).
-              if (NPASS > 1) lo[j] = pack_f16x2_rn_relu(x[2 * j] - __uint_as_float(__float_as_uint(x[2 * j]) & 0xFFFFE000u),
-                                                        x[2 * j + 1] - __uint_as_float(__float_as_uint(x[2 * j + 1]) & 0xFFFFE000u));
+              // lo = x - hi (hi = x rounded toward zero, ReLU folded in: lo >= 0 wherever x > 0, and for x <= 0 the
+              // second relu-conversion gives 0)
+              if (NPASS > 1) {
+#ifdef BH_EXP_MASKLO     // round-1 form: mantissa mask + FADD (ALU pipe)
+                lo[j] = pack_f16x2_rn_relu(x[2 * j] - __uint_as_float(__float_as_uint(x[2 * j]) & 0xFFFFE000u),
+                                           x[2 * j + 1] - __uint_as_float(__float_as_uint(x[2 * j + 1]) & 0xFFFFE000u));
+#else
+                float r0, r1;
+                f16x2_residual(hi[j], x[2 * j], x[2 * j + 1], r0, r1);
+                lo[j] = pack_f16x2_rn_relu(r0, r1);
+#endif
+              }
             }
             if (RANGE) {
 #pragma unroll
@@ -545,12 +572,14 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tbase, 512);
-  if (tid == 0 && *abort_s) atomicExch(status, 1);
-  if (tid == 0 && abort_s[1]) atomicExch(status + 3, 1);
+  if (tid == 0 && *abort_s) raise_flag(status, 0);
+  if (tid == 0 && abort_s[1]) raise_flag(status, 3);
 }
 
+// __maxnreg__ instead of __launch_bounds__: with the latter ptxas settles on 96 registers for 576 threads and spills the
+// epilogue; 112 x 576 still fits the register file (64512 of 65536) and compiles spill-free
 template <int NPASS, int SAVE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(112)
 tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, const float* __restrict__ t_frames,
               int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];

@@ -39,11 +39,16 @@ __host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { 
 #define TC_STAGE_MAX 81920u
 
 // ---- global workspace (bh_tc_ws_bytes) -------------------------------------------------------
-//   [0,256)        int32 status words (0 = ok)
+//   [0,256)        int32 status words (0 = ok): [0..5) flags of the CURRENT step (reset by tc_prepare_weights_kernel;
+//                  the guarded Adam kernels read them), [8..55) optional cycle counters, [55] magic, [56..61) the same
+//                  flags STICKY: set by any step since the last bhnerf_workspace_status call, which clears them
 //   [256,4096)     fp32 constants: b0,b1,b2,b3 (4x128) | W4 (128) | b4 (1)
 //   [4096, +224K)  fp16 weight images of the forward, per layer [hi plane | lo plane]; then 2 x 4 KB bias images
 //   [262144,+224K) bf16 weight images of the dgrad chain (cotangents need the fp32 exponent range), same layout
 #define TC_WS_STATUS 0u
+#define TC_STATUS_MAGIC_WORD 55
+#define TC_STATUS_MAGIC 0x62683230
+#define TC_STATUS_STICKY 56
 #define TC_WS_CONST 256u
 #define TC_WS_W 4096u
 #define TC_WS_WB 262144u
@@ -73,6 +78,12 @@ __host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { 
 
 namespace tc {
 using namespace umma;
+
+// raise health flag k of this step and its sticky copy
+__device__ __forceinline__ void raise_flag(int* status, int k) {
+  atomicExch(status + k, 1);
+  atomicExch(status + TC_STATUS_STICKY + k, 1);
+}
 
 // ---- abortable waits: a wedged pipeline flags an error and drains instead of hanging the GPU ----
 struct Abort { volatile int* flag; };

@@ -4,6 +4,7 @@ PyTorch is used for device memory and streams only; every compute step below is 
 libbhnerf_b200.so (hand-written CUDA for sm_100a).  Nothing here falls back to torch math."""
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -46,16 +47,39 @@ def _dev_f32(x, device):
     return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32)), device=device)
 
 
-_workspaces = {}
+_workspaces = {}          # device index -> current scratch tensor
+_ws_watch = {}            # device index -> weakrefs of every scratch tensor that may still be written (a captured CUDA graph
+                          # keeps writing health flags into the workspace it captured, even after a grow-only reallocation)
+_pending_flags = {}       # device index -> sticky flags read from a workspace when it was retired
+
+
+def _dev_key(device):
+    return device.index if device.index is not None else torch.cuda.current_device()
 
 
 def workspace(nbytes, device):
     """Grow-only per-device scratch (allocated off the hot path after the first step)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    key = _dev_key(device)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:                      # carry the retired buffer's sticky flags over (one sync, off the hot path)
+            _pending_flags[key] = [a | b for a, b in zip(_pending_flags.get(key, [0] * 8), _read_flags(ws, device))]
         _workspaces[key] = ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        ws[:256].zero_()                        # the caching allocator may hand back memory with stale status words
+        _ws_watch.setdefault(key, []).append(weakref.ref(ws))
     return ws
+
+
+def current_workspace(device):
+    """The scratch tensor the next C-ABI step on `device` will use (None before the first step)."""
+    return _workspaces.get(_dev_key(torch.device(device)))
+
+
+def _read_flags(ws, device):
+    flags = (C.c_int32 * 8)()
+    with torch.cuda.device(device):
+        check(_lib.load().bhnerf_workspace_status(_ptr(ws), flags, _stream()))
+    return list(flags)
 
 
 STATUS_FLAGS = ('forward pipeline aborted', 'dgrad chain aborted', 'wgrad aborted',
@@ -63,21 +87,25 @@ STATUS_FLAGS = ('forward pipeline aborted', 'dgrad chain aborted', 'wgrad aborte
                 'backward produced a non-finite parameter gradient')
 
 
-def workspace_status(device=None, impl=None):
-    """Health flags of the last tcgen05 step on `device` (C ABI: bhnerf_workspace_status).  Synchronises the
-    stream: call it off the hot path (Optimizer.run polls it when it logs).  Raises BhnerfError if a flag is set."""
+def workspace_status(device=None, impl=None, raise_on_error=True):
+    """Health flags of the tcgen05 steps on `device` since the previous call (C ABI: bhnerf_workspace_status; the flags are
+    sticky and cleared by the read).  Every workspace that can still be written is polled -- the current one and any a
+    captured CUDA graph holds.  Synchronises the stream: call it off the hot path (Optimizer.run polls it when it logs).
+    Raises BhnerfError if a flag is set (or returns the flags with raise_on_error=False)."""
     if resolve_impl(impl) != IMPL_TC:
         return [0] * 8
     device = torch.device(device if device is not None else 'cuda')
-    ws = _workspaces.get(device.index if device.index is not None else torch.cuda.current_device())
-    if ws is None:
-        return [0] * 8
-    flags = (C.c_int32 * 8)()
-    with torch.cuda.device(device):
-        check(_lib.load().bhnerf_workspace_status(_ptr(ws), flags, _stream()))
-    flags = list(flags)
+    key = _dev_key(device)
+    flags = _pending_flags.pop(key, [0] * 8)
+    live = []
+    for r in _ws_watch.get(key, []):
+        ws = r()
+        if ws is not None:
+            live.append(r)
+            flags = [a | b for a, b in zip(flags, _read_flags(ws, device))]
+    _ws_watch[key] = live
     bad = [STATUS_FLAGS[i] for i in range(len(STATUS_FLAGS)) if flags[i]]
-    if bad:
+    if bad and raise_on_error:
         raise _lib.BhnerfError('bhnerf_b200 tcgen05 step failed: ' + '; '.join(bad))
     return flags
 
@@ -348,11 +376,18 @@ def frames_per_chunk(scene, Bt, impl=None, max_workspace=None):
 
 
 def adam_step(params, grads, mu, nu, count, lr_init=1e-4, lr_final=1e-6, num_iters=5000, b1=0.9, b2=0.999,
-              eps=1e-8, grad_scale=1.0):
-    """In-place optax.adam + linear schedule on the flat buffers.  C ABI: bhnerf_adam_step."""
+              eps=1e-8, grad_scale=1.0, guard=None):
+    """In-place optax.adam + linear schedule on the flat buffers.  C ABI: bhnerf_adam_step.  `guard`: the tcgen05
+    workspace whose health flags veto the update (None = unguarded)."""
     lib = _lib.load()
     with torch.cuda.device(params.device):
         check(lib.bhnerf_adam_step(_ptr(params), _ptr(grads), _ptr(mu), _ptr(nu), params.numel(), int(count),
                                    float(lr_init), float(lr_final), int(num_iters), float(b1), float(b2), float(eps),
-                                   float(grad_scale), _stream()))
+                                   float(grad_scale), _ptr(guard), _stream()))
     return params
+
+
+def step_guard(device, impl=None):
+    """Workspace to pass as `guard` to the Adam update that follows a render step of kernel family `impl` (tcgen05 only:
+    the fp32 SIMT family keeps weights, not flags, at the head of its scratch)."""
+    return current_workspace(device) if resolve_impl(impl) == IMPL_TC else None

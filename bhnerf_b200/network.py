@@ -60,10 +60,11 @@ class TrainState:
     def params(self):
         return self.predictor._unflatten(self.flat)
 
-    def apply_gradients(self, grads, grad_scale=1.0):
-        """optax.adam + polynomial_schedule(lr_init, lr_final, 1, num_iters) (network.py:173-174,:621)."""
+    def apply_gradients(self, grads, grad_scale=1.0, guard=None):
+        """optax.adam + polynomial_schedule(lr_init, lr_final, 1, num_iters) (network.py:173-174,:621).  `guard`: tcgen05
+        workspace whose health flags veto the update (engine.step_guard)."""
         engine.adam_step(self.flat, grads, self.mu, self.nu, self.step, self.lr_init, self.lr_final,
-                         self.num_iters, grad_scale=grad_scale)
+                         self.num_iters, grad_scale=grad_scale, guard=guard)
         self.step += 1
         return self
 
@@ -330,26 +331,46 @@ def loss_fn_image(params, predictor_fn, target, sigma, offset, t_frames, coords,
 
 
 def _eht_prepare(scene, target, sigma, A, dtype, Bt):
+    """Shape checks of loss_fn_eht (network.py:542-559) and the flattening the C ABI takes.  The reference multiplies
+    ``A (nt, [npol,] nvis, npix)`` with the image vectors ``(nt, [npol,] npix, 1)`` -- one DFT matrix per frame AND
+    polarization (optimization.py:235-251 stacks them on axis 1) -- so the pol axis folds into the frame axis:
+    returns A as (nt*S, rows, npix) with rows = nvis ('vis','amp') or 3*ncphase ('cphase')."""
     if dtype not in ('vis', 'amp', 'cphase'):
         raise AttributeError('eht dtype ({}) not supported'.format(dtype))
-    if scene.S != 1:
-        raise NotImplementedError('polarized visibilities (A with a pol axis) are not built yet')
     A = engine._c64(A, scene.device)
     tshape = tuple(np.shape(target)) if not isinstance(target, torch.Tensor) else tuple(target.shape)
+    S = scene.S
+    pol = scene.polarized and not (S == 1 and A.dim() == (4 if dtype == 'cphase' else 3))
+    lead = (Bt, S) if pol else (Bt,)
+    want_ndim = len(lead) + (3 if dtype == 'cphase' else 2)
+    if not scene.polarized and S != 1:
+        raise AttributeError('images have {} Stokes channels but A has no polarization axis'.format(S))
+    if A.dim() != want_ndim or tuple(A.shape[:len(lead)]) != lead or A.shape[-1] != scene.P or \
+            (dtype == 'cphase' and A.shape[-3] != 3):
+        raise AttributeError('A should have shape {} = {}, got {}'.format(
+            '(nt, [npol,] 3, ncphase, npix)' if dtype == 'cphase' else '(nt, [npol,] nvis, npix)',
+            lead + ((3, 'V', scene.P) if dtype == 'cphase' else ('V', scene.P)), tuple(A.shape)))
+    vis_ndim = len(lead) + (2 if dtype == 'cphase' else 1)
     if dtype == 'cphase':
-        # A (nt, 3, ncphase, npix): one DFT matrix per baseline of each triangle (network.py:555-559)
-        if A.dim() != 4 or A.shape[0] != Bt or A.shape[1] != 3 or A.shape[3] != scene.P:
-            raise AttributeError('A should have shape (nt, 3, ncphase, npix) = ({}, 3, V, {}), got {}'.format(
-                Bt, scene.P, tuple(A.shape)))
-        if len(tshape) != 2:
-            raise AttributeError('visibilities (ndim=3) should have +1 dimensions as target (ndim={}) for dtype={}'.format(
-                len(tshape), dtype))
-        return A.reshape(Bt, 3 * A.shape[2], scene.P)      # triangle axis folded into the row axis
-    if A.dim() != 3 or A.shape[0] != Bt or A.shape[2] != scene.P:
-        raise AttributeError('A should have shape (nt, nvis, npix) = ({}, V, {}), got {}'.format(Bt, scene.P, tuple(A.shape)))
-    if len(tshape) != 2:
-        raise AttributeError('visibilities (ndim=2) should have same dimensions as target (ndim={}) for dtype={}'.format(len(tshape), dtype))
-    return A
+        if len(tshape) + 1 != vis_ndim:
+            raise AttributeError('visibilities (ndim={}) should have +1 dimensions as target (ndim={}) for dtype={}'.format(
+                vis_ndim, len(tshape), dtype))
+        return A.reshape(Bt * (S if pol else 1), 3 * A.shape[-2], scene.P)      # triangle axis folded into the row axis
+    if len(tshape) != vis_ndim:
+        raise AttributeError('visibilities (ndim={}) should have same dimensions as target (ndim={}) for dtype={}'.format(
+            vis_ndim, len(tshape), dtype))
+    return A.reshape(Bt * (S if pol else 1), A.shape[-2], scene.P)
+
+
+def _eht_sigma(sigma, target, device):
+    """sigma broadcast to the target's shape (the reference divides by it with numpy broadcasting)."""
+    sig = engine._dev_f32(sigma, device)
+    return sig.expand(target.shape).contiguous() if sig.shape != target.shape else sig
+
+
+def _eht_rows(x, n):
+    """target / sigma of an eht loss as (n, -1) rows (n = frames x polarizations)."""
+    return x.reshape(n, -1)
 
 
 def loss_fn_eht(params, predictor_fn, target, sigma, A, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs,
@@ -361,8 +382,10 @@ def loss_fn_eht(params, predictor_fn, target, sigma, A, t_frames, coords, Omega,
                          scene.device).reshape(-1)
     A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
     images, _, _ = pred._render_fwd(scene, _flat(params, scene.device, pred), tf, impl)
-    vis = engine.vis_fwd(A, images)
-    loss, _ = engine.loss_vis(vis, target, sigma, float(scale), dtype)
+    n = A.shape[0]                                           # frames x polarizations
+    vis = engine.vis_fwd(A, images.reshape(n, 1, scene.P))
+    tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
+    loss, _ = engine.loss_vis(vis, _eht_rows(tgt, n), _eht_rows(_eht_sigma(sigma, tgt, scene.device), n), float(scale), dtype)
     return loss, [_shape_images(images, scene, J)]
 
 
@@ -373,7 +396,7 @@ def _dist():
     return None
 
 
-def _pmean_and_apply(state, grads, update=True):
+def _pmean_and_apply(state, grads, update=True, guard=None):
     """jax.lax.pmean(grads,'batch') + state.apply_gradients (network.py:620-621): all-reduce SUM over ranks,
     the 1/ndev is folded into the Adam kernel's grad_scale."""
     dist = _dist()
@@ -382,7 +405,10 @@ def _pmean_and_apply(state, grads, update=True):
         dist.all_reduce(grads, op=dist.ReduceOp.SUM)
         scale = 1.0 / dist.get_world_size()
     if update:
-        state.apply_gradients(grads, grad_scale=scale)
+        if guard is not None:
+            state.apply_gradients(grads, grad_scale=scale, guard=guard)
+        else:
+            state.apply_gradients(grads, grad_scale=scale)
     return state
 
 
@@ -428,7 +454,7 @@ class _GraphedImageStep:
             engine.check(lib.bhnerf_adam_step_dev(engine._ptr(state.flat), engine._ptr(self.out[2]), engine._ptr(state.mu),
                                                   engine._ptr(state.nu), state.flat.numel(), engine._ptr(self.count),
                                                   state.lr_init, state.lr_final, state.num_iters, 0.9, 0.999, 1e-8, 1.0,
-                                                  engine._stream()))
+                                                  engine._ptr(engine.step_guard(dev, impl)), engine._stream()))
         # warm-up outside the capture (lazy module load, function attributes, workspace growth), on saved copies so that
         # it leaves the optimiser state untouched
         keep = [t.clone() for t in (state.flat, state.mu, state.nu, self.count)]
@@ -514,7 +540,8 @@ def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, 
         grads = pred._render_bwd(scene, state.flat, tf, dI)
     else:
         loss, images, grads = engine.train_step_image(scene, state.flat, tf, tgt, sig, off, float(scale), dtype, impl)
-    state = _pmean_and_apply(state, grads)
+    guard = engine.step_guard(scene.device, impl) if isinstance(pred, NeRF_Predictor) else None
+    state = _pmean_and_apply(state, grads, guard=guard)
     return loss, state, _shape_images(images, scene, J)
 
 
@@ -539,20 +566,25 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
     Bt = tf.numel()
     Bc = Bt if isinstance(pred, GRID_Predictor) else engine.frames_per_chunk(scene, Bt, impl)
     tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
-    sig = engine._dev_f32(sigma, scene.device)
+    sig = _eht_sigma(sigma, tgt, scene.device)
+    npol = A.shape[0] // Bt                                   # DFT matrices per frame (1, or one per Stokes channel)
+    tgt, sig = _eht_rows(tgt, Bt * npol), _eht_rows(sig, Bt * npol)
     loss, grads, imgs = None, None, []
     for b0 in range(0, Bt, Bc):
         sl = slice(b0, min(b0 + Bc, Bt))
+        rows = slice(b0 * npol, min(b0 + Bc, Bt) * npol)
         images, e, acts = pred._render_fwd(scene, state.flat, tf[sl], impl, save_acts=not isinstance(pred, GRID_Predictor))
-        vis = engine.vis_fwd(A[sl].contiguous(), images)
-        l, dvis = engine.loss_vis(vis, tgt[sl], sig[sl], float(scale), dtype)
-        dI = engine.vis_bwd(A[sl].contiguous(), dvis, scene.P)
+        A_c = A[rows].contiguous()
+        vis = engine.vis_fwd(A_c, images.reshape(A_c.shape[0], 1, scene.P))
+        l, dvis = engine.loss_vis(vis, tgt[rows], sig[rows], float(scale), dtype)
+        dI = engine.vis_bwd(A_c, dvis, scene.P).reshape(images.shape)
         g = pred._render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)
         loss = l if loss is None else engine.add_inplace(loss, l)       # per-chunk partials accumulate on the device
         grads = g if grads is None else engine.add_inplace(grads, g)
         imgs.append(images)
     images = imgs[0] if len(imgs) == 1 else torch.cat(imgs, dim=0)
-    state = _pmean_and_apply(state, grads)
+    guard = engine.step_guard(scene.device, impl) if isinstance(pred, NeRF_Predictor) else None
+    state = _pmean_and_apply(state, grads, guard=guard)
     return loss, state, _shape_images(images, scene, J)
 
 

@@ -180,13 +180,44 @@ class TrainStep(object):
         return cls(dtype, args, network.gradient_step_image, network.test_image, scale)
 
     @classmethod
-    def eht(cls, t_frames, target, sigma, A, dtype='vis', scale=1.0):
-        """optimization.py:218-268 minus the ehtim calls: the reference builds (target, sigma, A) with
-        ``ehtim.imaging.imager_utils.chisqdata_<dtype>`` (third party, absent here); they are inputs of
-        the hot path, so this constructor takes them directly.  A: (nt, nvis, npix) complex64."""
+    def eht(cls, t_frames, obs, image_fov, image_size, chisqdata, pol='I', scale=1.0):
+        """optimization.py:218-268, same signature and steps: split the ehtim observation into per-frame scans, build the
+        square prior image, call ``chisqdata(obs_frame, prior, mask=[], pol=p)`` (ehtim.imaging.imager_utils.chisqdata_vis /
+        _amp / _cphase) per frame and polarization, stack the polarizations on axis 1 and squeeze, convert ehtim's
+        closure phases from degrees to radians (:253-255).  ehtim is a third-party package that is not vendored by the
+        reference: ``obs`` only needs ``split_obs`` and ``ehtim.image.make_square`` must be importable.  When (target,
+        sigma, A) are already at hand use :meth:`eht_arrays`."""
+        from ehtim.image import make_square
+        dtype = chisqdata.__name__.split('_')[-1]
+        pol_types = ['I', 'Q', 'U']
+        span = t_frames[-1] - t_frames[0]
+        span_s = span.to('s').value if hasattr(span, 'to') else float(span) * 3600.0      # unit-less frames are hours
+        obs_frames = obs.split_obs(t_gather=span_s / (len(t_frames) + 1))
+        prior = make_square(obs, image_size, image_fov)
+        target, sigma, A = [], [], []
+        for p in np.atleast_1d(pol):
+            if p not in pol_types:
+                raise AttributeError('pol ({}) not in supported pol_types: {},{},{}'.format(p, *pol_types))
+            target_p, sigma_p, A_p = [np.array(out) for out in zip(*[chisqdata(o, prior, mask=[], pol=p) for o in obs_frames])]
+            target.append(target_p); sigma.append(sigma_p); A.append(A_p)
+        target, sigma, A = (np.squeeze(np.stack(target, axis=1)), np.squeeze(np.stack(sigma, axis=1)),
+                            np.squeeze(np.stack(A, axis=1)))
+        return cls.eht_arrays(t_frames, target, sigma, A, dtype=dtype, scale=scale, degrees=(dtype == 'cphase'))
+
+    @classmethod
+    def eht_arrays(cls, t_frames, target, sigma, A, dtype='vis', scale=1.0, degrees=False):
+        """The reference's ``TrainStep.eht`` after its ehtim calls: (target, sigma, A) as ehtim's chisqdata_<dtype> returns
+        them, stacked per frame.  A: (nt, nvis, npix) complex64, or (nt, npol, nvis, npix) for several polarizations
+        (optimization.py:235-251; target / sigma then carry the same pol axis), or (nt, [npol,] 3, ncphase, npix) for closure
+        phases.  ``degrees=True`` applies the reference's np.deg2rad to closure-phase targets and sigmas (:253-255: ehtim
+        reports them in degrees); pass radians otherwise."""
         target = np.asarray(target)
-        args = TemporalBatchedArgs(t_frames, [target, np.asarray(sigma, dtype=np.float32),
-                                              np.asarray(A, dtype=np.complex64)])
+        sigma = np.asarray(sigma, dtype=np.float32)
+        if degrees:
+            if dtype != 'cphase':
+                raise AttributeError('degrees=True only applies to closure phases (dtype=cphase)')
+            target, sigma = np.deg2rad(target), np.deg2rad(sigma).astype(np.float32)
+        args = TemporalBatchedArgs(t_frames, [target, sigma, np.asarray(A, dtype=np.complex64)])
         return cls(dtype, args, network.gradient_step_eht, network.test_eht, scale)
 
     @property
@@ -223,9 +254,10 @@ def _flax_ext_hook(code, data):
     if code == 1:
         shape, dtype, buf = msgpack.unpackb(data, raw=True)
         return np.frombuffer(buf, dtype=np.dtype(dtype.decode() if isinstance(dtype, bytes) else dtype)).reshape(shape).copy()
-    if code == 3:
-        dtype, buf = msgpack.unpackb(data, raw=True)
-        return np.frombuffer(buf, dtype=np.dtype(dtype.decode() if isinstance(dtype, bytes) else dtype))[0]
+    if code == 3:      # numpy scalar: flax packs it as the 0-d array np.asarray(x) -- the same (shape, dtype, bytes) triple
+        shape, dtype, buf = msgpack.unpackb(data, raw=True)
+        arr = np.frombuffer(buf, dtype=np.dtype(dtype.decode() if isinstance(dtype, bytes) else dtype)).reshape(shape)
+        return arr[()]
     if code == 2:
         re_, im_ = msgpack.unpackb(data)
         return complex(re_, im_)
@@ -264,14 +296,28 @@ def save_checkpoint(checkpoint_dir, state, step, keep=5, fmt=None):
     the earlier pickled dict), same ``keep`` policy."""
     fmt = fmt or os.environ.get('BHNERF_CHECKPOINT_FORMAT', 'flax')
     os.makedirs(checkpoint_dir, exist_ok=True)
-    with open(os.path.join(checkpoint_dir, 'checkpoint_%d' % step), 'wb') as f:
-        if fmt == 'pickle':
+    final = os.path.join(checkpoint_dir, 'checkpoint_%d' % step)
+    tmp = os.path.join(checkpoint_dir, '.tmp_checkpoint_%d_%d' % (step, os.getpid()))
+    with open(tmp, 'wb') as f:                     # written aside and renamed: an interrupted save never leaves a
+        if fmt == 'pickle':                        # truncated file that restore_checkpoint would pick as the latest
             pickle.dump(state.state_dict(), f)
         else:
             f.write(state_to_flax_bytes(state))
-    ck = sorted([int(n.split('_')[1]) for n in os.listdir(checkpoint_dir) if n.startswith('checkpoint_')])
-    for s in ck[:-keep]:
+        f.flush()
+        os.fsync(f.fileno())
+    os.replace(tmp, final)
+    for s in _checkpoint_steps(checkpoint_dir)[:-keep]:
         os.remove(os.path.join(checkpoint_dir, 'checkpoint_%d' % s))
+
+
+def _checkpoint_steps(checkpoint_dir):
+    """Sorted steps of the ``checkpoint_<step>`` files of a directory (anything else, e.g. ``checkpoint_tmp``, is ignored)."""
+    out = []
+    for n in os.listdir(checkpoint_dir):
+        parts = n.split('_')
+        if len(parts) == 2 and parts[0] == 'checkpoint' and parts[1].isdigit():
+            out.append(int(parts[1]))
+    return sorted(out)
 
 
 def restore_checkpoint(checkpoint_dir, state):
@@ -279,8 +325,7 @@ def restore_checkpoint(checkpoint_dir, state):
     flax msgpack or the earlier pickle payload (detected by the pickle protocol marker)."""
     if not os.path.isdir(checkpoint_dir):
         return state
-    ck = sorted([int(n.split('_')[1]) for n in os.listdir(checkpoint_dir)
-                 if n.startswith('checkpoint_') and n.split('_')[1].isdigit()])
+    ck = _checkpoint_steps(checkpoint_dir)
     if not ck:
         return state
     with open(os.path.join(checkpoint_dir, 'checkpoint_%d' % ck[-1]), 'rb') as f:
@@ -307,6 +352,7 @@ class Optimizer(object):
         self.loss = np.inf
         self.keep = keep
         self.seed = hparams.get('seed', 1)
+        self.status_period = int(hparams.get('status_period', 100))
         params = predictor.init_params(raytracing_args, seed=self.seed)
         self.state = predictor.init_state(params=params, num_iters=self.num_iters,
                                           lr_init=hparams.get('lr_init', 1e-4), lr_final=hparams.get('lr_final', 1e-6),
@@ -315,12 +361,30 @@ class Optimizer(object):
             predictor.save_params(checkpoint_dir)
 
     def log(self):
+        fired = False
         for log_fn in self.log_fns:
-            log_fn(self)
+            fired = bool(log_fn(self)) or fired
+        # health flags at log cadence (the log functions read the loss, i.e. synchronise, anyway) and every
+        # `status_period` steps regardless; the flags are sticky, so an overflow on ANY step in between is seen
+        if fired or (self.step % self.status_period == 0):
+            self.check_health()
+
+    def check_health(self):
+        """Raise on every rank if any rank's tcgen05 steps flagged an overflow / abort since the last check.  The Adam
+        kernels are guarded by the same flags, so the flagged gradient itself was never applied."""
+        flags = engine.workspace_status(device=self.state.flat.device, raise_on_error=False)
+        bad = torch.tensor([1.0 if any(flags[:5]) else 0.0], device=self.state.flat.device)
+        if _world()[1] > 1:
+            import torch.distributed as dist
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)        # collective: no rank runs ahead into the next all-reduce
+        if bad.item() > 0:
+            mine = [engine.STATUS_FLAGS[i] for i in range(5) if flags[i]]
+            raise engine._lib.BhnerfError('bhnerf_b200 tcgen05 step failed at or before step %d: %s' % (
+                self.step, '; '.join(mine) if mine else 'flagged on another rank'))
 
     def save_checkpoint(self):
         if (self.checkpoint_dir != '') and ((self.step % self.save_period == 0) or (self.step == self.final_step)):
-            engine.workspace_status()       # never checkpoint a state an overflowed tcgen05 step produced (raises)
+            self.check_health()             # never checkpoint a state an overflowed tcgen05 step produced (raises)
             if _world()[0] == 0:
                 save_checkpoint(self.checkpoint_dir, self.state, int(self.step), keep=self.keep)
 
@@ -338,7 +402,7 @@ class Optimizer(object):
                 self.save_checkpoint()
         except KeyboardInterrupt:
             return
-        engine.workspace_status()           # health flags of the last step (one sync, off the hot loop)
+        self.check_health()                 # flags raised since the last poll (one sync, off the hot loop)
 
     @property
     def params(self):
@@ -356,3 +420,5 @@ class LogFn(object):
         if self.log_period > 0:
             if (optimizer.step == 1) or ((optimizer.step % self.log_period) == 0):
                 self.log_fn(optimizer)
+                return True
+        return False

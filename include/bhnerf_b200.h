@@ -182,18 +182,20 @@ int bhnerf_geodesic_inputs(const double* r, const double* theta, const double* p
 /* ---- optimiser: optax.adam + polynomial_schedule(power=1) applied by
  * TrainState.apply_gradients (bhnerf/network.py:171-182, :621).  grad_scale multiplies the
  * gradient first (1/ndev turns an all-reduce SUM into jax.lax.pmean, network.py:620).
- * count = number of updates already applied.                                                 */
+ * count = number of updates already applied.  guard (or NULL): device pointer to the health flags of the step
+ * that produced `grads` (= the tcgen05 workspace, see bhnerf_workspace_status); if one is set the update is
+ * skipped, so a gradient from an overflowed or aborted step is never applied.                */
 /* dst[n] += src[n] on the device (per-chunk gradients / losses of the chunked eht step) */
 int bhnerf_add_inplace(float* dst, const float* src, int32_t n, void* stream);
 int bhnerf_adam_step(float* params, const float* grads, float* mu, float* nu, int32_t n,
                      int32_t count, float lr_init, float lr_final, int32_t transition_steps,
-                     float b1, float b2, float eps, float grad_scale, void* stream);
+                     float b1, float b2, float eps, float grad_scale, const int32_t* guard, void* stream);
 
 /* The same update with the step counter in device memory (*count_dev is read, then advanced by one): nothing in the
  * call depends on host state, so a whole train step can be captured in a CUDA graph and replayed.                */
 int bhnerf_adam_step_dev(float* params, const float* grads, float* mu, float* nu, int32_t n,
                          int32_t* count_dev, float lr_init, float lr_final, int32_t transition_steps,
-                         float b1, float b2, float eps, float grad_scale, void* stream);
+                         float b1, float b2, float eps, float grad_scale, const int32_t* guard, void* stream);
 
 /* ---- accounting for benchmarks: kernels launched by this library, and (between begin/end) CUDA-event
  * time per category {0 render fwd, 1 render bwd, 2 wgrad (SIMT only), 3 heads, 4 misc}.
@@ -202,13 +204,14 @@ int64_t bhnerf_launch_count(void);
 int bhnerf_profile_begin(void);
 int bhnerf_profile_end(double* ms_host, int64_t* scopes_host, int64_t* launches_host);
 
-/* ---- health flags of the last tcgen05 step that used `workspace` (the first bytes of every TC workspace;
- * reset by the next step).  Synchronises `stream`.  flags_host[8]:
+/* ---- health flags of the tcgen05 steps that used `workspace` (kept in its first 256 bytes).  The flags are STICKY: one
+ * raised by any step since the previous call is reported, then cleared by this call.  (The current step's own copy, words
+ * [0..5) of the workspace, is what the guarded Adam update looks at.)  Synchronises `stream`.  flags_host[8]:
  *   [0] forward pipeline aborted (a bounded mbarrier wait expired)   [1] dgrad chain aborted   [2] wgrad aborted
  *   [3] forward: |activation| exceeded the fp16 operand range (65504) -> images invalid
  *   [4] backward: non-finite parameter gradient (cotangent overflow)  [5..7] reserved (0)
  * The reference has no counterpart (XLA fp32 cannot overflow here); callers poll this off the hot path.        */
-int bhnerf_workspace_status(const void* workspace, int32_t* flags_host, void* stream);
+int bhnerf_workspace_status(void* workspace, int32_t* flags_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,44 @@
+"""Issue-rate probe of the epilogue instruction mix (bhnerf_b200/csrc/epi_probe.cu): cycles per warp-instruction per
+SMSP for each op alone and for pairs (sum of the single rates = same pipe, max = different pipes).
+Usage (GPU box): python scripts/run_epi_probe.py"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+so = os.path.join(ge.LIBDIR, 'libbhnerf_epi_probe.so')
+src = os.path.join(ge.CSRC, 'epi_probe.cu')
+if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+    subprocess.check_call(['/usr/local/cuda/bin/nvcc'] + ge.NVCC_FLAGS + ['-o', so, src])
+lib = C.CDLL(so)
+lib.epi_probe_run.restype = C.c_int
+lib.epi_probe_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+NAMES = {0: 'F2FP f16x2 rn', 1: 'F2FP f16x2 rz.relu', 2: 'F2FP bf16x2 rn.relu', 3: 'LOP3', 4: 'FADD', 5: 'HSET2 (set.gt.u32.f16x2)',
+         6: 'HADD2.F32 (cvt.f32.f16)', 7: 'PRMT', 8: 'FFMA', 9: 'FMNMX', 10: 'IMAD', 11: 'SHF', 12: 'F2FP e4m3x2',
+         20: 'F2FP + LOP3', 21: 'F2FP + FADD', 22: 'F2FP + HSET2', 23: 'F2FP + HADD2.F32', 24: 'LOP3 + FADD', 25: 'FADD + HSET2',
+         26: 'FADD + HADD2.F32', 27: 'LOP3 + PRMT', 28: 'F2FP + PRMT', 29: 'F2FP + FFMA', 30: 'LOP3 + HSET2', 31: 'LOP3 + HADD2.F32',
+         32: 'HSET2 + HADD2.F32', 33: 'F2FP f16 + F2FP bf16', 34: 'LOP3 + IMAD', 35: 'FADD + IMAD', 36: 'F2FP + IMAD',
+         50: 'fwd epilogue mix today (3 F2FP + 4 LOP3 + 2 FADD + HSET2)', 51: 'fp16 saves (2 F2FP + 3 LOP3 + 2 FADD + HSET2)',
+         52: 'fp16 saves, one residual via HADD2.F32 (2 F2FP + 2 LOP3 + 2 FADD + HSET2 + HADD2.F32)',
+         53: 'dgrad epilogue mix (F2FP + LOP3 + PRMT)'}
+seed = torch.randint(0, 2 ** 31 - 1, (256,), dtype=torch.int32, device='cuda')
+seed = (seed & 0x007fffff) | 0x3f000000          # floats in [0.5, 1): no NaN / denormal slow paths
+out = torch.zeros(148 * 512, dtype=torch.int32, device='cuda')
+cyc = torch.zeros(148, dtype=torch.int64, device='cuda')
+iters = 2000
+st = torch.cuda.current_stream().cuda_stream
+print('%-90s %10s %10s' % ('mix', 'cyc/instr', 'instr/clk'))
+for i in sorted(NAMES):
+    for _ in range(2):
+        n = lib.epi_probe_run(i, seed.data_ptr(), out.data_ptr(), iters, cyc.data_ptr(), st)
+        torch.cuda.synchronize()
+    assert n > 0
+    c = cyc.double().mean().item()
+    per_smsp = c / (iters * n * 4)      # 4 warps per SMSP issue n instructions per iteration each
+    print('%-90s %10.3f %10.3f' % (NAMES[i], per_smsp, 1.0 / per_smsp), flush=True)

@@ -168,3 +168,78 @@ def test_flax_msgpack_checkpoint_format_roundtrip(tmp_path):
     optimization.save_checkpoint(d2, state, 5, fmt='pickle')
     old = pred.init_state(pred.init_params(seed=9), num_iters=100, device='cpu', checkpoint_dir=d2)
     assert torch.equal(old.flat, state.flat) and old.step == 30
+
+
+def test_flax_numpy_scalar_ext_and_stray_checkpoint_files(tmp_path):
+    """(1) flax packs a numpy SCALAR (e.g. state.step / opt_state count as np.int32) as ExtType(3, msgpack((shape=(),
+    dtype, bytes))) -- the same triple as an ndarray, unpacked with arr[()]; a hand-built blob of that form must restore.
+    (2) files that merely start with 'checkpoint_' (tmp files, foreign suffixes) are ignored by both the keep policy and the
+    restore, and a save leaves no temporary file behind."""
+    import msgpack
+    import torch
+    from bhnerf_b200 import network, optimization
+    scal = msgpack.ExtType(3, msgpack.packb(([], 'int32', np.asarray(17, dtype=np.int32).tobytes()), use_bin_type=True))
+    back = msgpack.unpackb(msgpack.packb({'step': scal}, use_bin_type=True), ext_hook=optimization._flax_ext_hook, raw=False)
+    assert back['step'] == 17 and np.asarray(back['step']).dtype == np.int32 and np.ndim(back['step']) == 0
+    pred = network.NeRF_Predictor(8.0, 2.0, 8.0, 4.0)
+    state = pred.init_state(pred.init_params(seed=3), num_iters=100, device='cpu')
+    tree = msgpack.unpackb(optimization.state_to_flax_bytes(state), ext_hook=lambda c, d: msgpack.ExtType(c, d), raw=False)
+    tree['step'] = scal
+    tree['opt_state']['0']['count'] = scal
+    fresh = pred.init_state(pred.init_params(seed=9), num_iters=100, device='cpu')
+    optimization.state_from_flax_bytes(fresh, msgpack.packb(tree, use_bin_type=True))
+    assert fresh.step == 17 and torch.equal(fresh.flat, state.flat)
+    d = str(tmp_path / 'ck')
+    os.makedirs(d)
+    for stray in ('checkpoint_tmp', 'checkpoint_5.orbax', 'checkpoint_'):
+        open(os.path.join(d, stray), 'wb').write(b'junk')
+    for step in (1, 2, 3):
+        state.step = step
+        optimization.save_checkpoint(d, state, step, keep=2)
+    assert sorted(os.listdir(d)) == ['checkpoint_', 'checkpoint_2', 'checkpoint_3', 'checkpoint_5.orbax', 'checkpoint_tmp']
+    again = pred.init_state(pred.init_params(seed=9), num_iters=100, device='cpu', checkpoint_dir=d)
+    assert again.step == 3
+
+
+def test_trainstep_eht_reference_signature_with_a_duck_typed_observation(monkeypatch):
+    """TrainStep.eht(t_frames, obs, image_fov, image_size, chisqdata, pol, scale) -- the reference's signature
+    (optimization.py:218-268): per-frame split, chisqdata per frame and polarization, pol axis stacked on axis 1 and
+    squeezed, closure phases converted from ehtim's degrees.  ehtim itself is third party and absent: a stub module
+    provides make_square and the observation is duck-typed."""
+    import types
+    from bhnerf_b200 import optimization
+    calls = {}
+    ehtim = types.ModuleType('ehtim'); image = types.ModuleType('ehtim.image')
+    image.make_square = lambda obs, npix, fov: ('prior', npix, fov)
+    ehtim.image = image
+    monkeypatch.setitem(sys.modules, 'ehtim', ehtim); monkeypatch.setitem(sys.modules, 'ehtim.image', image)
+    nt, V, P = 5, 7, 16
+    rng = np.random.default_rng(0)
+
+    class Obs:
+        def split_obs(self, t_gather):
+            calls['t_gather'] = t_gather
+            return [('frame', i) for i in range(nt)]
+
+    def chisqdata_vis(obs, prior, mask=[], pol='I'):
+        k = 'IQU'.index(pol)
+        return (np.full(V, obs[1] + 10 * k, dtype=np.complex64), np.full(V, 1.0 + k, dtype=np.float32),
+                np.full((V, P), obs[1] + 100 * k, dtype=np.complex64))
+
+    def chisqdata_cphase(obs, prior, mask=[], pol='I'):
+        return (np.full(V, 90.0), np.full(V, 45.0), np.ones((3, V, P), dtype=np.complex64))
+
+    t = np.linspace(0.0, 2.0, nt)
+    ts = optimization.TrainStep.eht(t, Obs(), 1e-9, 4, chisqdata_vis)
+    assert ts.dtype[0] == 'vis' and abs(calls['t_gather'] - 2.0 * 3600 / (nt + 1)) < 1e-9
+    target, sigma, A, tf = ts.args[0].args
+    assert target.shape == (nt, V) and sigma.shape == (nt, V) and A.shape == (nt, V, P) and A.dtype == np.complex64
+    assert target[3, 0] == 3
+    ts3 = optimization.TrainStep.eht(t, Obs(), 1e-9, 4, chisqdata_vis, pol=['I', 'Q', 'U'])
+    target, sigma, A, tf = ts3.args[0].args
+    assert target.shape == (nt, 3, V) and A.shape == (nt, 3, V, P) and sigma[0, 2, 0] == 3.0 and A[2, 1, 0, 0] == 102
+    tsc = optimization.TrainStep.eht(t, Obs(), 1e-9, 4, chisqdata_cphase)
+    target, sigma, A, tf = tsc.args[0].args
+    assert tsc.dtype[0] == 'cphase' and np.allclose(target, np.pi / 2) and np.allclose(sigma, np.pi / 4) and A.shape == (nt, 3, V, P)
+    with pytest.raises(AttributeError):
+        optimization.TrainStep.eht(t, Obs(), 1e-9, 4, chisqdata_vis, pol='V')

@@ -182,7 +182,7 @@ def test_reference_api_eht_step_matches_oracle(dtype):
     state = pred.init_state(params, num_iters=100, lr_init=1e-3, lr_final=1e-5)
     rt = OrderedDict(coords=geo['coords'], Omega=geo['Omega'], J=1.0, g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
                      t_start_obs=float(d['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d['t_injection']))
-    ts = optimization.TrainStep.eht(d['t_frames'], d['target'], d['sigma'], d['A'], dtype=dtype)
+    ts = optimization.TrainStep.eht_arrays(d['t_frames'], d['target'], d['sigma'], d['A'], dtype=dtype)
     loss0, _, images = ts(state, rt, np.arange(4), update_state=False)
     assert abs(loss0.item() - float(d['loss'])) / abs(float(d['loss'])) < IMG_TOL
     assert np.abs(images.cpu().numpy() - d['images'].reshape(images.shape)).max() / np.abs(d['images']).max() < IMG_TOL
@@ -194,7 +194,48 @@ def test_reference_api_eht_step_matches_oracle(dtype):
     upd_err = np.abs((got - d['params_flat']) - (want - d['params_flat'])).max() / 1e-3
     assert upd_err < 2e-2, upd_err
     with pytest.raises(AttributeError):
-        optimization.TrainStep.eht(d['t_frames'], d['target'], d['sigma'], d['A'], dtype='bogus')(state, rt, np.arange(4))
+        optimization.TrainStep.eht_arrays(d['t_frames'], d['target'], d['sigma'], d['A'], dtype='bogus')(state, rt, np.arange(4))
+
+
+@pytest.mark.parametrize('impl', _impls())
+def test_polarized_visibilities_match_oracle(impl):
+    """A with a polarization axis (optimization.py:235-251 stacks I,Q,U on axis 1; network.py:542-548 multiplies each
+    Stokes image with its own DFT matrix): loss, visibilities, images and the first Adam update through
+    TrainStep.eht_arrays -> gradient_step_eht against the float64 oracle golden case_vis_IQU."""
+    from collections import OrderedDict
+    from bhnerf_b200 import engine, network, optimization
+    from oracle import bhnerf_oracle as O
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    d = np.load(os.path.join(G, 'case_vis_IQU.npz'))
+    pred = network.NeRF_Predictor(float(d['scale']), float(d['rmin']), float(d['rmax']), float(d['z_width']))
+    state = pred.init_state(network.unflatten_params(d['params_flat']), num_iters=100, lr_init=1e-3, lr_final=1e-5)
+    rt = OrderedDict(coords=geo['coords'], Omega=geo['Omega'], J=d['J'], g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
+                     t_start_obs=float(d['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d['t_injection']))
+    assert d['A'].shape == (4, 3, 12, 256) and d['target'].shape == (4, 3, 12)
+    # the visibilities themselves, through the C ABI with the pol axis folded into the frame axis
+    scene = network._scene_for(pred, *[rt[k] for k in ('coords', 'Omega', 'J', 'g', 'dtau', 'Sigma', 't_start_obs', 't_geos',
+                                                       't_injection')], 'hr', device=state.flat.device)
+    images, _, _ = engine.render_fwd(scene, state.flat, d['t_frames'].astype(np.float32), impl)
+    vis = engine.vis_fwd(engine._c64(d['A'], scene.device).reshape(12, 12, 256), images.reshape(12, 1, 256))
+    assert np.abs(vis.cpu().numpy().reshape(4, 3, 12) - d['vis']).max() / np.abs(d['vis']).max() < IMG_TOL
+    ts = optimization.TrainStep.eht_arrays(d['t_frames'], d['target'], d['sigma'], d['A'], dtype='vis')
+    loss0, _, images = network.test_eht(state, 'hr', 'vis', d['target'], d['sigma'], d['A'], d['t_frames'], *rt.values(), 1.0,
+                                        impl=impl)
+    assert abs(loss0.item() - float(d['loss'])) / float(d['loss']) < IMG_TOL
+    assert tuple(images.shape) == (4, 3, 16, 16)
+    assert np.abs(images.cpu().numpy() - d['images']).max() / np.abs(d['images']).max() < IMG_TOL
+    loss, state, _ = network.gradient_step_eht(state, 'hr', 'vis', d['target'], d['sigma'], d['A'], d['t_frames'],
+                                               *rt.values(), 1.0, impl=impl)
+    assert abs(loss.item() - float(d['loss'])) / float(d['loss']) < IMG_TOL
+    want, _, _ = O.adam_step(d['params_flat'].astype(np.float64), d['grads'], np.zeros(55169), np.zeros(55169), 0,
+                             1e-3, 1e-5, 100)
+    got = state.flat.cpu().numpy()
+    upd_err = np.abs((got - d['params_flat']) - (want - d['params_flat'])).max() / 1e-3
+    assert upd_err < 2e-2, upd_err
+    loss_ts, _, _ = ts(state, rt, np.arange(4), update_state=False)      # the TrainStep route accepts the same arrays
+    assert np.isfinite(loss_ts.item())
+    with pytest.raises(AttributeError):      # Stokes images but an A without the pol axis: the reference's matmul cannot broadcast
+        network.test_eht(state, 'hr', 'vis', d['target'][:, 0], d['sigma'][:, 0], d['A'][:, 0], d['t_frames'], *rt.values(), 1.0)
 
 
 def test_predictor_apply_and_sample_3d_grid_vs_oracle():
@@ -300,7 +341,9 @@ def test_simt_and_tc_agree_at_config_shape(nt):
 
 def test_fp16_operand_overflow_is_flagged_not_hidden():
     """The tcgen05 forward rounds hidden activations to fp16 operands.  Weights that push |h| past 65504 must raise
-    through bhnerf_workspace_status (status word 3), and healthy weights must leave every flag clear."""
+    through bhnerf_workspace_status (status word 3), healthy weights must leave every flag clear, the flag is STICKY (a
+    later healthy step does not hide it; it is reported once, then cleared), and the guarded Adam update refuses the
+    gradient of a flagged step."""
     from bhnerf_b200 import _lib, engine, testing
     scene, d = testing.load_golden_scene('case_image_full')
     tf = torch.as_tensor(d['t_frames'].astype(np.float32)).cuda()
@@ -311,10 +354,20 @@ def test_fp16_operand_overflow_is_flagged_not_hidden():
     bad[: 21 * 128 + 128] *= 3.0e4            # W0, b0: h0 ~ 3e4 x O(1..10)
     bad[21 * 128 + 128: 21 * 128 + 128 + 128 * 128] *= 30.0
     engine.render_fwd(scene, bad, tf, 'tc')
+    engine.render_fwd(scene, good, tf, 'tc')  # a healthy step in between: the per-step words are reset, the sticky ones not
     with pytest.raises(_lib.BhnerfError, match='fp16 operand range'):
         engine.workspace_status(impl='tc')
-    engine.render_fwd(scene, good, tf, 'tc')  # flags are per step
-    assert engine.workspace_status(impl='tc')[3] == 0
+    assert engine.workspace_status(impl='tc')[:5] == [0, 0, 0, 0, 0]      # reported once
+    # guarded Adam: the update after a flagged step leaves the parameters alone, after a healthy step it moves them
+    tgt = d['target']; one = np.ones_like(tgt); zero = np.zeros_like(tgt)
+    for params, moves in ((bad, False), (good, True)):
+        p = params.clone(); mu = torch.zeros_like(p); nu = torch.zeros_like(p)
+        _, _, grads = engine.train_step_image(scene, p, tf, tgt, one, zero, 1.0, 'full', 'tc')
+        engine.adam_step(p, grads, mu, nu, 0, 1e-3, 1e-5, 10, guard=engine.step_guard(scene.device, 'tc'))
+        torch.cuda.synchronize()
+        assert bool((p != params).any().item()) == moves
+    assert engine.workspace_status(impl='tc', raise_on_error=False)[3] == 1   # the flagged train step is on record
+    assert engine.workspace_status(impl='tc')[:5] == [0, 0, 0, 0, 0]
 
 
 def _geo_ns(geo, with_g=True):
@@ -597,7 +650,7 @@ def test_multi_loss_train_step_image_plus_visibilities():
     pred = network.NeRF_Predictor(prd['scale'], prd['rmin'], prd['rmax'], prd['z_width'])
     rt = OrderedDict(coords=geo['coords'], Omega=geo['Omega'], J=1.0, g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
                      t_start_obs=float(d1['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d1['t_injection']))
-    ts = optimization.TrainStep.image(d1['t_frames'], d1['target'], sigma=1.0, dtype='full') + optimization.TrainStep.eht(
+    ts = optimization.TrainStep.image(d1['t_frames'], d1['target'], sigma=1.0, dtype='full') + optimization.TrainStep.eht_arrays(
         d2['t_frames'], d2['target'], d2['sigma'], d2['A'], dtype='vis', scale=1.0)
     assert ts.num_losses == 2
     state = pred.init_state(network.unflatten_params(d1['params_flat']), num_iters=100, lr_init=1e-3, lr_final=1e-5)

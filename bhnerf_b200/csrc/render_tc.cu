@@ -1,17 +1,20 @@
 // tcgen05 forward render kernel (sm_100a): warp -> posenc -> 4x128 MLP on the 5th-gen tensor cores
-// (bf16x3 split operands, fp32 accumulate in TMEM) -> sigmoid(o-10) -> masked emission.
+// (fp16 x3 split operands, fp32 accumulate in TMEM) -> sigmoid(o-10) -> masked emission.
 // Reference semantics: bhnerf/network.py:18-64 (MLP), :98-122 (posenc), :191-237 (NeRF_Predictor.__call__),
 // bhnerf/emission.py:143-211 (velocity_warp_coords).  DESIGN.md s4 describes the pipeline.
 //
-// One persistent CTA per SM, 10 warps:
-//   warps 0-3  epilogue of tile slot 0 (TMEM lane quadrant = warp%4; thread = one sample row)
-//   warps 4-7  epilogue of tile slot 1
-//   warp  8    MMA issuer (one elected lane issues every tcgen05.mma / tcgen05.commit)
-//   warp  9    weight producer (cp.async.bulk of the next layer's [hi|lo] weight images into a 2-stage ring)
+// One persistent CTA per SM, 20 warps:
+//   warps 0-7   epilogue of tile slot 0: (column half) x (TMEM lane quadrant = warp%4); thread = one sample row x 64 columns
+//   warps 8-15  epilogue of tile slot 1
+//   warp  16    MMA issuer (one elected lane issues every tcgen05.mma / tcgen05.commit)
+//   warp  17    weight producer (cp.async.bulk of the next layer's [hi|lo] weight images into a 2-stage ring)
+//   warps 18-19 idle (they complete the fifth warpgroup for setmaxnreg)
 // Two 128-sample tiles are in flight per CTA and ping-pong: while the tensor core runs layer l of one tile,
-// the CUDA cores run the bias+ReLU+hi/lo-split epilogue of the other.  Activations never leave the SM:
+// the CUDA cores run the ReLU + hi/lo-split epilogue of the other.  Activations never leave the SM:
 // D (fp32) is read from TMEM with tcgen05.ld and the next layer's A operand is written back to TMEM with
 // tcgen05.st (TS-form MMA); only the 21 posenc features go through shared memory (SS-form, K-major).
+// The features of a slot's NEXT tile are computed while its current tile waits for the tensor core (double-buffered
+// feature images), so the ~3 k cycles of warp + posenc are off the tile's serial chain.
 #include <cuda_fp16.h>
 #include <type_traits>
 #include <stdlib.h>
@@ -21,15 +24,34 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 576;            // 16 epilogue warps + MMA issuer + weight producer
+// 16 epilogue warps + MMA issuer + weight producer + 2 idle warps that complete the fifth warpgroup (setmaxnreg is a
+// warpgroup-wide instruction).  Registers: every SM sub-partition hosts 4 epilogue warps + 1 other warp; the kernel launches
+// at 96 per thread (5 x 96 = 480 per lane of a sub-partition, the pool setmaxnreg redistributes) and rebalances to
+// 4 x 104 + 64: the epilogue holds 64 accumulator values + both operand planes and spilled at 96.
+constexpr int kThreads = 640;
+constexpr int kEpiRegs = 104, kAuxRegs = 64;
 constexpr int kMmaWarp = 16;
-constexpr uint32_t SM_WSTAGE = 0;                                  // 2 x 80 KB weight ring
-constexpr uint32_t SM_FEAT = 2 * TC_STAGE_MAX;                     // 2 slots x [hi 8K | lo 8K]
-constexpr uint32_t SM_CONST = SM_FEAT + 2 * 2 * TC_FIMG_BYTES;     // 768 floats
-constexpr uint32_t SM_BARS = SM_CONST + TC_CONST_FLOATS * 4;       // 8 mbarriers + tmem base + abort flag
-constexpr uint32_t SM_TOTAL = SM_BARS + 128;
+// forward weight images in the workspace (fp16, [hi plane | lo plane] each), tc_prepare_weights_kernel:
+//   L0 (K = 32: 21 features, 2 bias rows) | L1 | L2 | L3 rows 0..127 (hidden part) | L3 rows 128..159 (skip part, K = 32)
+// The skip part is its own image so that it can stay resident in shared memory: the ring stages then need 64 KB (+ a 4 KB
+// bias image) instead of 80 KB, which pays for the second set of feature images.
+__host__ __device__ constexpr uint32_t fw_K(int j) { return (j == 0 || j == 4) ? 32u : 128u; }
+__host__ __device__ constexpr uint32_t fw_plane(int j) { return fw_K(j) * 128u * 2u; }
+__host__ __device__ constexpr uint32_t fw_off(int j) {
+  return j == 0 ? 0u : (j == 1 ? 16384u : (j == 2 ? 81920u : (j == 3 ? 147456u : 212992u)));
+}
+static_assert(fw_off(4) + 2u * fw_plane(4) == TC_W_BYTES, "forward weight block");
+constexpr uint32_t FW_STAGE = 65536u + TC_BIMG_BYTES;              // one ring stage: [hi | lo] (<= 64 KB) + bias image
+constexpr uint32_t SM_WSTAGE = 0;                                  // 2 ring stages
+constexpr uint32_t SM_WSKIP = 2 * FW_STAGE;                        // resident [hi 8K | lo 8K] skip rows of layer 3
+constexpr uint32_t SM_FEAT = SM_WSKIP + 2 * fw_plane(4);           // [slot][buffer][hi 8K | lo 8K]
+constexpr uint32_t SM_CONST = SM_FEAT + 2 * 2 * 2 * TC_FIMG_BYTES; // 768 floats
+constexpr uint32_t SM_BARS = SM_CONST + TC_CONST_FLOATS * 4;       // mbarriers + tmem base + abort flags
+constexpr uint32_t SM_PART = SM_BARS + 256;                        // [slot][row] partial of the last layer
+constexpr uint32_t SM_TOTAL2 = SM_PART + 2 * 128 * 4;
+static_assert(SM_TOTAL2 <= 232448, "forward shared memory");
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_AREADY = 4, BAR_DREADY = 6 };
+enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_AREADY = 4, BAR_DREADY = 6, BAR_FREADY = 8, BAR_DFREE = 10, BAR_SKIP = 12, BAR_COUNT = 13 };
 
 // ------------------------------------------------------------------------------------------------
 // weight images: fp32 params -> bf16 hi/lo planes in the canonical UMMA layout (tc_common.cuh)
@@ -107,12 +129,15 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ params, uint
     *reinterpret_cast<__half*>(bimg + img_off(k, n, TC_IMG_RS, 2u * 128u)) = __float2half_rn(wb);
   }
   uint32_t off = img_off(k, n, TC_IMG_RS, (uint32_t)(K / 8) * 128u);
-  {   // forward: fp16 hi/lo planes
+  {   // forward: fp16 hi/lo planes; layer 3 as two images (rows 0..127 | rows 128..159, see fw_off)
     __half hi = __float2half_rn(w);
     __half lo = __float2half_rn(w - __half2float(hi));
-    uint8_t* base = ws + TC_WS_W + tc_stage_off(l);
-    *reinterpret_cast<__half*>(base + off) = hi;
-    *reinterpret_cast<__half*>(base + tc_plane_bytes(l) + off) = lo;
+    const int j = (l == 3 && k >= 128) ? 4 : l;
+    const int kk = (j == 4) ? k - 128 : k;
+    const uint32_t foff = img_off(kk, n, TC_IMG_RS, (fw_K(j) / 8u) * 128u);
+    uint8_t* base = ws + TC_WS_W + fw_off(j);
+    *reinterpret_cast<__half*>(base + foff) = hi;
+    *reinterpret_cast<__half*>(base + fw_plane(j) + foff) = lo;
   }
   {   // dgrad chain: bf16 hi/lo planes
     __nv_bfloat16 hi = __float2bfloat16_rn(w);
@@ -131,8 +156,8 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ params, uint
 // ------------------------------------------------------------------------------------------------
 template <int NPASS, int L>
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t tmem_a, uint32_t feat_smem, uint32_t w_smem,
-                                            uint32_t idesc) {
-  constexpr uint32_t K = tc_layer_K(L), plane = tc_plane_bytes(L), w_cs = (K / 8) * 128u;
+                                            uint32_t skip_smem, uint32_t idesc) {
+  constexpr uint32_t K = fw_K(L), plane = fw_plane(L), w_cs = (K / 8) * 128u;
   constexpr int nks = (int)(K / 16);
   // B: image [k][n] read MN-major: K groups advance by RS (LBO), N groups by CS (SBO)
   const uint32_t b_hi = desc_hi(w_cs);
@@ -147,12 +172,17 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t tmem_a, ui
     for (int ks = 0; ks < nks; ++ks) {
       const uint32_t bl = b_lo[wp] + (uint32_t)ks * ((2u * TC_IMG_RS) >> 4);
       const uint32_t acc = (pass | ks) ? 1u : 0u;
-      if (L == 0 || (L == 3 && ks >= 8)) {
-        const int kk = (L == 0) ? ks : ks - 8;
-        mma_ss_raw(tmem_d, a_lo[ap] + (uint32_t)kk * ((2u * TC_SIMG_CS) >> 4), a_hi, bl, b_hi, idesc, acc);
-      } else {
-        mma_ts_raw(tmem_d, tmem_a + (uint32_t)ap * 64u + (uint32_t)ks * 8u, bl, b_hi, idesc, acc);
-      }
+      if (L == 0) mma_ss_raw(tmem_d, a_lo[ap] + (uint32_t)ks * ((2u * TC_SIMG_CS) >> 4), a_hi, bl, b_hi, idesc, acc);
+      else mma_ts_raw(tmem_d, tmem_a + (uint32_t)ap * 64u + (uint32_t)ks * 8u, bl, b_hi, idesc, acc);
+    }
+    if (L == 3) {     // skip connection: [features] x W3 rows 128..159 (the resident K = 32 image; its rows 21, 22 carry b3)
+      constexpr uint32_t s_plane = fw_plane(4), s_cs = (fw_K(4) / 8) * 128u;
+      const uint32_t sb_hi = desc_hi(s_cs);
+      const uint32_t sb_lo = desc_lo(skip_smem + (uint32_t)wp * s_plane, TC_IMG_RS);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma_ss_raw(tmem_d, a_lo[ap] + (uint32_t)ks * ((2u * TC_SIMG_CS) >> 4), a_hi, sb_lo + (uint32_t)ks * ((2u * TC_IMG_RS) >> 4),
+                   sb_hi, idesc, 1u);
     }
   }
   if (L == 1 || L == 2)      // + [feature cols 16..31] x bias image: adds b_hi + b_lo through the two constant-1 columns
@@ -194,10 +224,6 @@ __device__ __forceinline__ float safe_sin_fast(float a) {      // same float32 A
 #else
   return sin_reduced_mufu(r);
 #endif
-}
-
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
 // warped + scaled coordinates of one sample (bh_features without the encodings)
@@ -242,12 +268,6 @@ __device__ __forceinline__ void f16x2_residual(uint32_t hi, float x0, float x1, 
       : "=f"(r0), "=f"(r1) : "r"(hi), "f"(x0), "f"(x1));
 }
 
-constexpr uint32_t SM_PART = SM_BARS + 128;                        // [slot][row] partial of the last layer
-// inputs of every thread's NEXT sample (x, y, z, Omega, t_geos, ray, t_frame), staged by cp.async: [slot][half][7][128]
-constexpr uint32_t SM_INBUF = SM_PART + 2 * 128 * 4;
-constexpr uint32_t SM_TOTAL2 = SM_INBUF + 2 * 2 * 7 * 128 * 4;
-static_assert(SM_TOTAL2 <= 232448, "forward shared memory");
-
 // SAVE = bf16 planes of every activation kept for the backward (0, 1, 2).  RANGE = track max|h| per sample: compiled
 // as a second body of the same kernel and entered only when the weight bound of tc_prepare_weights_kernel cannot
 // rule out an fp16 operand overflow (the tracking costs ~10 % of the forward, so the usual path does not carry it).
@@ -257,10 +277,11 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
             const float* __restrict__ t_frames, int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts,
             int* __restrict__ status) {
   uint8_t* wst = smem + SM_WSTAGE;
-  uint8_t* featimg = smem + SM_FEAT;
+  uint8_t* wskip = smem + SM_WSKIP;
+  uint8_t* featimg = smem + SM_FEAT;                  // [slot][buffer][plane] x 8 KB
   float* cst = (float*)(smem + SM_CONST);
   uint64_t* bars = (uint64_t*)(smem + SM_BARS);
-  uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
+  uint32_t* tmem_base_s = (uint32_t*)(bars + BAR_COUNT);
   int* abort_s = (int*)(tmem_base_s + 1);
   float* part = (float*)(smem + SM_PART);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -273,21 +294,29 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
     mbar_init(&bars[BAR_WEMPTY + 0], 1); mbar_init(&bars[BAR_WEMPTY + 1], 1);
     mbar_init(&bars[BAR_AREADY + 0], 8); mbar_init(&bars[BAR_AREADY + 1], 8);
     mbar_init(&bars[BAR_DREADY + 0], 1); mbar_init(&bars[BAR_DREADY + 1], 1);
+    mbar_init(&bars[BAR_FREADY + 0], 8); mbar_init(&bars[BAR_FREADY + 1], 8);
+    mbar_init(&bars[BAR_DFREE + 0], 8); mbar_init(&bars[BAR_DFREE + 1], 8);
+    mbar_init(&bars[BAR_SKIP], 1);
     abort_s[0] = 0; abort_s[1] = 0;
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_base_s, 512);
   for (int i = tid; i < TC_CONST_FLOATS; i += kThreads) cst[i] = ((const float*)(ws + TC_WS_CONST))[i];
-  for (int i = tid; i < (int)(2 * 2 * TC_FIMG_BYTES / 16); i += kThreads)      // feature columns 24..31 stay zero
+  for (int i = tid; i < (int)(2 * 2 * 2 * TC_FIMG_BYTES / 16); i += kThreads)   // feature columns 24..31 stay zero
     reinterpret_cast<uint4*>(featimg)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tbase = *tmem_base_s;
 
-  if (warp == kMmaWarp + 1) {
+  if (warp > kMmaWarp + 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));      // idle warps of the last warpgroup
+  } else if (warp == kMmaWarp + 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
     // ===================== weight producer =====================
     if (lane == 0) {
+      mbar_expect_tx(&bars[BAR_SKIP], 2u * fw_plane(4));                      // resident skip rows of layer 3, once
+      bulk_g2s(wskip, ws + TC_WS_W + fw_off(4), 2u * fw_plane(4), &bars[BAR_SKIP]);
       uint32_t wcnt = 0;
       for (int r = 0;; ++r) {
         int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
@@ -298,10 +327,11 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
           ok = wait(&bars[BAR_WEMPTY + st], ((wcnt >> 1) & 1u) ^ 1u, ab);
           if (!ok) break;
           const bool bimg = (l == 1 || l == 2);
-          mbar_expect_tx(&bars[BAR_WFULL + st], tc_stage_bytes(l) + (bimg ? TC_BIMG_BYTES : 0u));
-          bulk_g2s(wst + st * TC_STAGE_MAX, ws + TC_WS_W + tc_stage_off(l), tc_stage_bytes(l), &bars[BAR_WFULL + st]);
+          const uint32_t bytes = 2u * fw_plane(l);
+          mbar_expect_tx(&bars[BAR_WFULL + st], bytes + (bimg ? TC_BIMG_BYTES : 0u));
+          bulk_g2s(wst + st * FW_STAGE, ws + TC_WS_W + fw_off(l), bytes, &bars[BAR_WFULL + st]);
           if (bimg)
-            bulk_g2s(wst + st * TC_STAGE_MAX + tc_stage_bytes(l), ws + TC_WS_W + TC_W_BYTES + (uint32_t)(l - 1) * TC_BIMG_BYTES,
+            bulk_g2s(wst + st * FW_STAGE + bytes, ws + TC_WS_W + TC_W_BYTES + (uint32_t)(l - 1) * TC_BIMG_BYTES,
                      TC_BIMG_BYTES, &bars[BAR_WFULL + st]);
         }
         if (!ok) break;
@@ -309,13 +339,14 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
     // ===================== MMA issuer: the whole warp runs the control flow, one elected lane issues =====================
     {
       const uint32_t idesc = make_idesc_f16(128, 128, 0, 1);
-      uint32_t wcnt = 0, a_phase[2] = {0u, 0u};
+      uint32_t wcnt = 0, a_phase[2] = {0u, 0u}, f_phase[2] = {0u, 0u}, df_phase[2] = {0u, 0u};
       BH_TIMING_T0 BH_TIMING_DECL(t_ww) BH_TIMING_DECL(t_wa) BH_TIMING_DECL(t_is)
-      bool ok = true;
-      auto layer_step = [&](auto Ltag, int T0) {
+      bool ok = wait(&bars[BAR_SKIP], 0, ab);
+      auto layer_step = [&](auto Ltag, int T0, int r) {
         constexpr int L = decltype(Ltag)::value;
         uint32_t st = wcnt & 1u;
         BH_TIMING_BEGIN
@@ -324,15 +355,24 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
         for (int s = 0; s < 2 && ok; ++s) {
           if (T0 + s >= NT) continue;
           BH_TIMING_BEGIN
-          ok = wait(&bars[BAR_AREADY + s], a_phase[s], ab);
+          if (L == 0) {
+            // layer 0 of a tile needs its feature image (written one tile ahead) and, from the slot's second tile on, the
+            // accumulator: the previous tile's layer-3 result must be in the epilogue warps' registers
+            ok = wait(&bars[BAR_FREADY + s], f_phase[s], ab);
+            f_phase[s] ^= 1u;
+            if (ok && r > 0) { ok = wait(&bars[BAR_DFREE + s], df_phase[s], ab); df_phase[s] ^= 1u; }
+          } else {
+            ok = wait(&bars[BAR_AREADY + s], a_phase[s], ab);
+            a_phase[s] ^= 1u;
+          }
           BH_TIMING_END(t_wa)
           if (!ok) break;
-          a_phase[s] ^= 1u;
           tc_fence_after_sync();
           BH_TIMING_BEGIN
           if (elect_one()) {
             issue_layer<NPASS, L>(tbase + (uint32_t)s * 256u, tbase + (uint32_t)s * 256u + 128u,
-                                  smem_u32(featimg + s * 2 * TC_FIMG_BYTES), smem_u32(wst + st * TC_STAGE_MAX), idesc);
+                                  smem_u32(featimg + (s * 2 + (r & 1)) * 2 * TC_FIMG_BYTES), smem_u32(wst + st * FW_STAGE),
+                                  smem_u32(wskip), idesc);
             mma_commit_raw(&bars[BAR_DREADY + s]);
           }
           __syncwarp();
@@ -347,40 +387,110 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
       for (int r = 0; ok; ++r) {
         int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
         if (T0 >= NT) break;
-        layer_step(std::integral_constant<int, 0>{}, T0);
-        layer_step(std::integral_constant<int, 1>{}, T0);
-        layer_step(std::integral_constant<int, 2>{}, T0);
-        layer_step(std::integral_constant<int, 3>{}, T0);
+        layer_step(std::integral_constant<int, 0>{}, T0, r);
+        layer_step(std::integral_constant<int, 1>{}, T0, r);
+        layer_step(std::integral_constant<int, 2>{}, T0, r);
+        layer_step(std::integral_constant<int, 3>{}, T0, r);
       }
       if (lane == 0) { BH_TIMING_STORE(status, 8, t_ww) BH_TIMING_STORE(status, 10, t_wa) BH_TIMING_STORE(status, 12, t_is) }
     }
     __syncwarp();
   } else {
     // ===================== epilogue warps: (slot, column half, lane quadrant) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     const int slot = warp >> 3, half = (warp >> 2) & 1, q = warp & 3, row = q * 32 + lane;
     const uint32_t t_lane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 256u;
-    uint8_t* my_feat = featimg + slot * 2 * TC_FIMG_BYTES;
     const uint32_t pair_bar = 1u + (uint32_t)(slot * 4 + q);          // named barrier of the two warps of a row
     uint32_t d_phase = 0;
     bool ok = true;
-    // inputs of the first tile; later tiles are prefetched one round ahead
-    // The next tile's inputs are fetched one round ahead with cp.async into this thread's own shared-memory words (no
-    // barrier: a thread reads back only what it copied).  Holding them in registers instead does not work under the
-    // 96-register cap of this kernel: they were spilled right after the loads, which made the "prefetch" synchronous
-    // (ncu: the top long-scoreboard stalls of the kernel after the barrier spins).
-    float* in_s = reinterpret_cast<float*>(smem + SM_INBUF) + (size_t)((slot * 2 + half) * 7) * 128 + row;
-    auto load_inputs = [&](int r) {
-      int T = (r * (int)gridDim.x + (int)blockIdx.x) * 2 + slot;
-      if (T < NT) {
-        const int b = T / tiles_per_frame, i = (T - b * tiles_per_frame) * 128 + row;
-        cp_async4(in_s + 0 * 128, v.x + i); cp_async4(in_s + 1 * 128, v.y + i); cp_async4(in_s + 2 * 128, v.z + i);
-        cp_async4(in_s + 3 * 128, v.omega + i); cp_async4(in_s + 4 * 128, v.tgeo + i); cp_async4(in_s + 5 * 128, v.ray + i);
-        cp_async4(in_s + 6 * 128, t_frames + b);
+    auto tile_of = [&](int r) { return (r * (int)gridDim.x + (int)blockIdx.x) * 2 + slot; };
+    // ---- features of the slot's tile of round r: warp + posenc in registers -> feature image buffer (r & 1).  Half 0 of a
+    // row writes u and the sines (cols 0..11), half 1 the cosines and the two constant-1 columns (12..22).  Runs one tile
+    // AHEAD of the MLP, while the current tile waits for the tensor core.  Returns valid / ray of the sample.
+    auto features = [&](int r, bool& valid, int& ray) {
+      const int T = tile_of(r), b = T / tiles_per_frame, tile = T - b * tiles_per_frame, i = tile * 128 + row;
+      float u[3];
+      ray = v.ray[i];
+      valid = warp_coords(v.x[i], v.y[i], v.z[i], v.omega[i], v.tgeo[i], bh_frame_time(t_frames[b], fc), fc, u);
+      // the weight bound of tc_prepare_weights_kernel assumes |coords/scale| <= 4 (the reference uses scale = rmax, i.e.
+      // <= 1): outside it the fp16 operand range cannot be vouched for without tracking
+      if (!RANGE && fmaxf(fmaxf(fabsf(u[0]), fabsf(u[1])), fabsf(u[2])) > 4.f) abort_s[1] = 1;
+      uint8_t* my_feat = featimg + (slot * 2 + (r & 1)) * 2 * TC_FIMG_BYTES;
+      float f[16];
+      if (half == 0) {
+        f[0] = u[0]; f[1] = u[1]; f[2] = u[2];
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[3 + 3 * ii + c] = safe_sin_fast(u[c] * (float)(1 << ii));
+        f[12] = f[13] = f[14] = f[15] = 0.f;
+      } else {
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            f[4 + 3 * ii + c] = safe_sin_fast(__fadd_rn(u[c] * (float)(1 << ii), BH_HALFPI_F));     // cols 12..20
+        f[0] = f[1] = f[2] = f[3] = 0.f;
+        f[13] = f[14] = 1.f;             // cols 21, 22 = 1: the weight rows they meet carry the bias (hi, lo parts)
+        f[15] = 0.f;
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      // half 0: chunk 0 (cols 0..7) + first 8 bytes of chunk 1 (cols 8..11)
+      // half 1: last 8 bytes of chunk 1 (cols 12..15) + chunk 2 (cols 16..23) [+ zero chunk 3 of the saved copy]
+      uint4 hA, lA, hB, lB;
+      split8_f16(f, hA, lA);
+      split8_f16(f + 8, hB, lB);
+      const uint32_t o0 = sample_img_off(row, 0), o1 = sample_img_off(row, 1), o2 = sample_img_off(row, 2);
+      if (half == 0) {
+        *reinterpret_cast<uint4*>(my_feat + o0) = hA;
+        *reinterpret_cast<uint2*>(my_feat + o1) = make_uint2(hB.x, hB.y);
+        if (NPASS > 1) {
+          *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + o0) = lA;
+          *reinterpret_cast<uint2*>(my_feat + TC_FIMG_BYTES + o1) = make_uint2(lB.x, lB.y);
+        }
+      } else {
+        *reinterpret_cast<uint2*>(my_feat + o1 + 8) = make_uint2(hA.z, hA.w);
+        *reinterpret_cast<uint4*>(my_feat + o2) = hB;
+        if (NPASS > 1) {
+          *reinterpret_cast<uint2*>(my_feat + TC_FIMG_BYTES + o1 + 8) = make_uint2(lA.z, lA.w);
+          *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + o2) = lB;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_FREADY + slot]);
+      if (SAVE) {                                       // the backward's operands are bf16 (range of the cotangents);
+        uint8_t* feat_save = acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + (size_t)v.n_pad * 1024u * SAVE +
+                             (size_t)tile * TC_FIMG_BYTES;
+        if (half == 1) f[14] = 0.f;                     // its copy keeps ONE constant-1 column: wgrad reads d bias off it
+        split8(f, hA, lA);
+        split8(f + 8, hB, lB);
+        const size_t lo_off = (size_t)v.n_pad * 64u;
+        if (half == 0) {
+          *reinterpret_cast<uint4*>(feat_save + o0) = hA;
+          *reinterpret_cast<uint2*>(feat_save + o1) = make_uint2(hB.x, hB.y);
+          if (SAVE == 2) {
+            *reinterpret_cast<uint4*>(feat_save + lo_off + o0) = lA;
+            *reinterpret_cast<uint2*>(feat_save + lo_off + o1) = make_uint2(lB.x, lB.y);
+          }
+        } else {
+          *reinterpret_cast<uint2*>(feat_save + o1 + 8) = make_uint2(hA.z, hA.w);
+          *reinterpret_cast<uint4*>(feat_save + o2) = hB;
+          *reinterpret_cast<uint4*>(feat_save + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
+          if (SAVE == 2) {
+            *reinterpret_cast<uint2*>(feat_save + lo_off + o1 + 8) = make_uint2(lA.z, lA.w);
+            *reinterpret_cast<uint4*>(feat_save + lo_off + o2) = lB;
+            *reinterpret_cast<uint4*>(feat_save + lo_off + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
     };
-    load_inputs(0);
     BH_TIMING_T0 BH_TIMING_DECL(t_ft) BH_TIMING_DECL(t_wd) BH_TIMING_DECL(t_ep)
+    bool n_valid = false; int n_ray = -1;               // of the tile whose features were computed last
+    if (tile_of(0) < NT) {                              // first tile of this slot: nothing to hide under yet
+      BH_TIMING_BEGIN
+      features(0, n_valid, n_ray);
+      BH_TIMING_END(t_ft)
+    }
     for (int r = 0; ok; ++r) {
       int T0 = (r * (int)gridDim.x + (int)blockIdx.x) * 2;
       if (T0 >= NT) break;
@@ -388,90 +498,8 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
       if (T >= NT) continue;
       const int b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
       const int i = tile * 128 + row;
-      // ---- warp + posenc in registers: half 0 writes u and the sines (cols 0..11), half 1 the cosines (12..20) ----
-      BH_TIMING_BEGIN
-      float u[3];
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      const float in_x = in_s[0 * 128], in_y = in_s[1 * 128], in_z = in_s[2 * 128], in_om = in_s[3 * 128],
-                  in_tg = in_s[4 * 128], in_tf = in_s[6 * 128];
-      const int in_ray = __float_as_int(in_s[5 * 128]);
-      const bool valid = warp_coords(in_x, in_y, in_z, in_om, in_tg, bh_frame_time(in_tf, fc), fc, u);
-      // the activation bound of tc_prepare_weights_kernel assumes |feature| <= 1; outside it, track the range per sample
-      // the weight bound assumes |coords/scale| <= 4 (the reference uses scale = rmax, i.e. <= 1): outside it the range
-      // cannot be vouched for without tracking
-      if (!RANGE && fmaxf(fmaxf(fabsf(u[0]), fabsf(u[1])), fabsf(u[2])) > 4.f) abort_s[1] = 1;
-      const int ray = in_ray;
-      load_inputs(r + 1);
-      uint8_t* feat_save = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) +
-                                      (size_t)v.n_pad * 1024u * SAVE + (size_t)tile * TC_FIMG_BYTES : nullptr;
-      {
-        float f[16];
-        if (half == 0) {
-          f[0] = u[0]; f[1] = u[1]; f[2] = u[2];
-#pragma unroll
-          for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) f[3 + 3 * ii + c] = safe_sin_fast(u[c] * (float)(1 << ii));
-          f[12] = f[13] = f[14] = f[15] = 0.f;
-        } else {
-#pragma unroll
-          for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              f[4 + 3 * ii + c] = safe_sin_fast(__fadd_rn(u[c] * (float)(1 << ii), BH_HALFPI_F));     // cols 12..20
-          f[0] = f[1] = f[2] = f[3] = 0.f;
-          f[13] = f[14] = 1.f;           // cols 21, 22 = 1: the weight rows they meet carry the bias (hi, lo parts)
-          f[15] = 0.f;
-        }
-        // half 0: chunk 0 (cols 0..7) + first 8 bytes of chunk 1 (cols 8..11)
-        // half 1: last 8 bytes of chunk 1 (cols 12..15) + chunk 2 (cols 16..23) [+ zero chunk 3 of the saved copy]
-        uint4 hA, lA, hB, lB;
-        split8_f16(f, hA, lA);
-        split8_f16(f + 8, hB, lB);
-        const uint32_t o0 = sample_img_off(row, 0), o1 = sample_img_off(row, 1), o2 = sample_img_off(row, 2);
-        if (half == 0) {
-          *reinterpret_cast<uint4*>(my_feat + o0) = hA;
-          *reinterpret_cast<uint2*>(my_feat + o1) = make_uint2(hB.x, hB.y);
-          if (NPASS > 1) {
-            *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + o0) = lA;
-            *reinterpret_cast<uint2*>(my_feat + TC_FIMG_BYTES + o1) = make_uint2(lB.x, lB.y);
-          }
-        } else {
-          *reinterpret_cast<uint2*>(my_feat + o1 + 8) = make_uint2(hA.z, hA.w);
-          *reinterpret_cast<uint4*>(my_feat + o2) = hB;
-          if (NPASS > 1) {
-            *reinterpret_cast<uint2*>(my_feat + TC_FIMG_BYTES + o1 + 8) = make_uint2(lA.z, lA.w);
-            *reinterpret_cast<uint4*>(my_feat + TC_FIMG_BYTES + o2) = lB;
-          }
-        }
-        if (SAVE) {                                     // the backward's operands are bf16 (range of the cotangents);
-          if (half == 1) f[14] = 0.f;                   // its copy keeps ONE constant-1 column: wgrad reads d bias off it
-          split8(f, hA, lA);
-          split8(f + 8, hB, lB);
-          const size_t lo_off = (size_t)v.n_pad * 64u;
-          if (half == 0) {
-            *reinterpret_cast<uint4*>(feat_save + o0) = hA;
-            *reinterpret_cast<uint2*>(feat_save + o1) = make_uint2(hB.x, hB.y);
-            if (SAVE == 2) {
-              *reinterpret_cast<uint4*>(feat_save + lo_off + o0) = lA;
-              *reinterpret_cast<uint2*>(feat_save + lo_off + o1) = make_uint2(lB.x, lB.y);
-            }
-          } else {
-            *reinterpret_cast<uint2*>(feat_save + o1 + 8) = make_uint2(hA.z, hA.w);
-            *reinterpret_cast<uint4*>(feat_save + o2) = hB;
-            *reinterpret_cast<uint4*>(feat_save + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
-            if (SAVE == 2) {
-              *reinterpret_cast<uint2*>(feat_save + lo_off + o1 + 8) = make_uint2(lA.z, lA.w);
-              *reinterpret_cast<uint4*>(feat_save + lo_off + o2) = lB;
-              *reinterpret_cast<uint4*>(feat_save + lo_off + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[BAR_AREADY + slot]);
-      BH_TIMING_END(t_ft)
+      const bool valid = n_valid; const int ray = n_ray;              // of THIS tile (computed one tile ago)
+      const bool has_next = tile_of(r + 1) < NT;
       uint8_t* act_tile = SAVE ? acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + (size_t)tile * TC_SIMG_BYTES : nullptr;
       float o = 0.f, xmax = 0.f;                        // xmax: largest activation written as an fp16 operand
       for (int l = 0; l < 4; ++l) {
@@ -489,6 +517,11 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
         tmem_ld32(t_lane + (uint32_t)(half * 64), raw[0]);
         tmem_ld32(t_lane + (uint32_t)(half * 64 + 32), raw[1]);
         tmem_wait_ld();
+        if (l == 3) {                                   // the accumulator is in registers: free for the next tile's layer 0
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[BAR_DFREE + slot]);
+        }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c0 = half * 64 + cc * 32;
@@ -552,6 +585,11 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
           *reinterpret_cast<uint2*>(acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + tc_mask_off(v.n_pad, SAVE) +
                                     tc_mask_word_off(tile, l, half, row)) = make_uint2(mword[0], mword[1]);
         BH_TIMING_END(t_ep)
+        if (l == 0 && has_next) {                       // the next tile's features, under the MMAs of layer 1 (and 2)
+          BH_TIMING_BEGIN
+          features(r + 1, n_valid, n_ray);
+          BH_TIMING_END(t_ft)
+        }
       }
       if (!ok) break;
       if (RANGE && xmax > 65504.f) abort_s[1] = 1;      // fp16 operand range exceeded (hi saturates): flag, do not hide
@@ -576,10 +614,8 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
   if (tid == 0 && abort_s[1]) raise_flag(status, 3);
 }
 
-// __maxnreg__ instead of __launch_bounds__: with the latter ptxas settles on 96 registers for 576 threads and spills the
-// epilogue; 112 x 576 still fits the register file (64512 of 65536) and compiles spill-free
 template <int NPASS, int SAVE>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(kThreads, 1)
 tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, const float* __restrict__ t_frames,
               int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];

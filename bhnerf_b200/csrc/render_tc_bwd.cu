@@ -512,7 +512,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 }
 
 template <int PL, bool WIDE>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(kDThreads, 1)
 tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
                 const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
                 float* __restrict__ d_params, int* __restrict__ status) {
@@ -837,7 +837,7 @@ constexpr uint32_t F_SM_TOTAL = D_SM_TOTAL > WCfg<1>::SM_TOTAL ? D_SM_TOTAL : WC
 // ND dgrad CTAs (cluster ranks 0..ND-1) feed ONE wgrad CTA (rank ND).  ND = 1 is the production shape (74 pairs, all
 // resident); ND = 2 is kept as a measured alternative (see bwd_dgrad_per_cluster).
 template <bool WIDE, int ND>
-__global__ void __cluster_dims__(ND + 1, 1, 1) __maxnreg__(112)
+__global__ void __cluster_dims__(ND + 1, 1, 1) __launch_bounds__(kDThreads, 1)
 tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
                     const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
                     float* __restrict__ d_params, int* __restrict__ status) {

@@ -98,3 +98,112 @@ extern "C" int epi_probe_run(int id, const uint32_t* seed, uint32_t* out, int it
     default: return 0;
   }
 }
+
+// =====================================================================================================
+// Stand-alone replica of the forward's layer epilogue (render_tc.cu): 16 warps, each thread one TMEM lane x 64 columns:
+// tcgen05.ld -> fp16 hi (rz, relu) / lo planes -> tcgen05.st -> relu bit masks -> saved hi plane to global memory.
+// No tensor core, no barriers: what the CUDA-core side of one SM can sustain, and which part of it costs what
+// (flags switch parts off).  cycles[blk] = cycles for `iters` tile-layers per slot (2 slots in parallel).
+// =====================================================================================================
+#include "umma.cuh"
+using namespace umma;
+enum { EF_LDTM = 1, EF_SPLIT = 2, EF_STTM = 4, EF_MASK = 8, EF_STG = 16, EF_LO = 32 };
+
+template <int FLAGS>
+__global__ void __launch_bounds__(512, 1) epi_full_kernel(uint8_t* __restrict__ gbuf, size_t gbytes, int iters,
+                                                          long long* __restrict__ cycles, uint32_t* __restrict__ sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const int slot = warp >> 3, half = (warp >> 2) & 1, q = warp & 3, row = q * 32 + lane;
+  const uint32_t t_lane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 256u;
+  // seed the accumulator columns with something that is not constant
+  {
+    uint32_t init[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) init[j] = __float_as_uint(0.001f * (float)((tid * 7 + j * 13) % 1000) - 0.3f);
+    for (int c = 0; c < 128; c += 16) tmem_st16(t_lane + (uint32_t)c, init);
+    tmem_wait_st();
+  }
+  __syncthreads();
+  uint32_t acc = 0, mw0 = 0, mw1 = 0;
+  const size_t per_iter = 2u * 32768u;                       // both slots' tile-layer images
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t raw[2][32];
+    if (FLAGS & EF_LDTM) {
+      tmem_ld32(t_lane + (uint32_t)(half * 64), raw[0]);
+      tmem_ld32(t_lane + (uint32_t)(half * 64 + 32), raw[1]);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { raw[0][j] = acc + j * 0x01010101u; raw[1][j] = acc ^ (j * 0x00100301u); }
+    }
+    uint8_t* act_img = gbuf + (((size_t)blockIdx.x * iters + it) * per_iter + (size_t)slot * 32768u) % gbytes;
+#pragma unroll
+    for (int sc = 0; sc < 4; ++sc) {
+      const int cc = sc >> 1, c0 = half * 64 + sc * 16, j0 = (sc & 1) * 8;
+      const uint32_t* rw = &raw[cc][(sc & 1) * 16];
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = __uint_as_float(rw[2 * j]), x1 = __uint_as_float(rw[2 * j + 1]);
+        if (FLAGS & EF_SPLIT) {
+          asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(x1), "f"(x0));
+          if (FLAGS & EF_LO) {
+            float r0, r1;
+            asm("{\n\t.reg .b16 l, u, m;\n\tmov.b32 {l, u}, %2;\n\tmov.b16 m, 0xBC00;\n\t"
+                "fma.rn.f32.f16 %0, l, m, %3;\n\tfma.rn.f32.f16 %1, u, m, %4;\n\t}" : "=f"(r0), "=f"(r1) : "r"(hi[j]), "f"(x0), "f"(x1));
+            asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(r1), "f"(r0));
+          } else lo[j] = rw[2 * j];
+        } else { hi[j] = rw[2 * j]; lo[j] = rw[2 * j + 1]; }
+      }
+      if (FLAGS & EF_STTM) {
+        tmem_st8(t_lane + 128u + (uint32_t)(c0 >> 1), hi);
+        tmem_st8(t_lane + 192u + (uint32_t)(c0 >> 1), lo);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc ^= lo[j];
+      }
+      if (FLAGS & EF_MASK) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t m = __hgt2_mask(*reinterpret_cast<const __half2*>(&hi[j]), __float2half2_rn(0.f)) &
+                             ((1u << (8 * ((j0 + j) & 1) + 7 - ((j0 + j) >> 1))) | (1u << (8 * ((j0 + j) & 1) + 7 - ((j0 + j) >> 1) + 16)));
+          if (cc) mw1 |= m; else mw0 |= m;
+        }
+      }
+      if (FLAGS & EF_STG) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          *reinterpret_cast<uint4*>(act_img + (uint32_t)(row >> 3) * 128u + (uint32_t)((c0 >> 3) + g) * 2048u + (uint32_t)(row & 7) * 16u) =
+              make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc ^= hi[j];
+      }
+    }
+    if (FLAGS & EF_STTM) { tmem_wait_st(); }
+  }
+  const long long t1 = clock64();
+  sink[blockIdx.x * blockDim.x + tid] = acc ^ mw0 ^ mw1;
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+extern "C" int epi_full_run(int flags, uint8_t* gbuf, size_t gbytes, int iters, long long* cycles, uint32_t* sink, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+#define EFCASE(F) case F: epi_full_kernel<F><<<148, 512, 0, st>>>(gbuf, gbytes, iters, cycles, sink); break;
+  switch (flags) {
+    EFCASE(63) EFCASE(63 - 16) EFCASE(63 - 8) EFCASE(63 - 8 - 16) EFCASE(63 - 4) EFCASE(63 - 1) EFCASE(1) EFCASE(1 + 4) EFCASE(2 + 32)
+    EFCASE(63 - 32) EFCASE(1 + 16) EFCASE(16) EFCASE(2 + 32 + 8)
+    default: return -1;
+  }
+  return (int)cudaGetLastError();
+}

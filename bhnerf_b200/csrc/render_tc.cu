@@ -407,14 +407,17 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
     // ---- features of the slot's tile of round r: warp + posenc in registers -> feature image buffer (r & 1).  Half 0 of a
     // row writes u and the sines (cols 0..11), half 1 the cosines and the two constant-1 columns (12..22).  Runs one tile
     // AHEAD of the MLP, while the current tile waits for the tensor core.  Returns valid / ray of the sample.
-    auto features = [&](int r, bool& valid, int& ray) {
+    float u[3] = {0.f, 0.f, 0.f};                       // warped, scaled coordinates between the two parts
+    auto features_a = [&](int r, bool& valid, int& ray) {
       const int T = tile_of(r), b = T / tiles_per_frame, tile = T - b * tiles_per_frame, i = tile * 128 + row;
-      float u[3];
       ray = v.ray[i];
       valid = warp_coords(v.x[i], v.y[i], v.z[i], v.omega[i], v.tgeo[i], bh_frame_time(t_frames[b], fc), fc, u);
       // the weight bound of tc_prepare_weights_kernel assumes |coords/scale| <= 4 (the reference uses scale = rmax, i.e.
       // <= 1): outside it the fp16 operand range cannot be vouched for without tracking
       if (!RANGE && fmaxf(fmaxf(fabsf(u[0]), fabsf(u[1])), fabsf(u[2])) > 4.f) abort_s[1] = 1;
+    };
+    auto features_b = [&](int r) {
+      const int T = tile_of(r), b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
       uint8_t* my_feat = featimg + (slot * 2 + (r & 1)) * 2 * TC_FIMG_BYTES;
       float f[16];
       if (half == 0) {
@@ -458,12 +461,18 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_FREADY + slot]);
-      if (SAVE) {                                       // the backward's operands are bf16 (range of the cotangents);
+      if (SAVE) {
+        // the backward's copy keeps ONE constant-1 column (21): wgrad reads d bias off it.  One-plane plan: the fp16 hi
+        // plane just computed (column 22 cleared); two-plane plan: bf16 hi + lo planes.
         uint8_t* feat_save = acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + (size_t)v.n_pad * 1024u * SAVE +
                              (size_t)tile * TC_FIMG_BYTES;
-        if (half == 1) f[14] = 0.f;                     // its copy keeps ONE constant-1 column: wgrad reads d bias off it
-        split8(f, hA, lA);
-        split8(f + 8, hB, lB);
+        if (SAVE == 2) {
+          if (half == 1) f[14] = 0.f;
+          split8(f, hA, lA);
+          split8(f + 8, hB, lB);
+        } else if (half == 1) {
+          hB.w = 0u;                                    // cols 22, 23
+        }
         const size_t lo_off = (size_t)v.n_pad * 64u;
         if (half == 0) {
           *reinterpret_cast<uint4*>(feat_save + o0) = hA;
@@ -473,13 +482,12 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
             *reinterpret_cast<uint2*>(feat_save + lo_off + o1) = make_uint2(lB.x, lB.y);
           }
         } else {
+          // (columns 24..31 of the saved copy are never written: the wgrad discards the accumulator columns they feed)
           *reinterpret_cast<uint2*>(feat_save + o1 + 8) = make_uint2(hA.z, hA.w);
           *reinterpret_cast<uint4*>(feat_save + o2) = hB;
-          *reinterpret_cast<uint4*>(feat_save + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
           if (SAVE == 2) {
             *reinterpret_cast<uint2*>(feat_save + lo_off + o1 + 8) = make_uint2(lA.z, lA.w);
             *reinterpret_cast<uint4*>(feat_save + lo_off + o2) = lB;
-            *reinterpret_cast<uint4*>(feat_save + lo_off + sample_img_off(row, 3)) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
       }
@@ -488,7 +496,8 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
     bool n_valid = false; int n_ray = -1;               // of the tile whose features were computed last
     if (tile_of(0) < NT) {                              // first tile of this slot: nothing to hide under yet
       BH_TIMING_BEGIN
-      features(0, n_valid, n_ray);
+      features_a(0, n_valid, n_ray);
+      features_b(0);
       BH_TIMING_END(t_ft)
     }
     for (int r = 0; ok; ++r) {
@@ -522,16 +531,19 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[BAR_DFREE + slot]);
         }
+        // 16 columns at a time (operand planes -> TMEM, saved copy -> global): short live ranges, the 64 accumulator values
+        // are the only large register block of the epilogue
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c0 = half * 64 + cc * 32;
-          float x[32];                                  // pre-activation (the bias came through the MMA)
+        for (int sc = 0; sc < 4; ++sc) {
+          const int cc = sc >> 1, c0 = half * 64 + sc * 16, j0 = (sc & 1) * 8;      // j0: first pair of the mask word
+          const uint32_t* rw = &raw[cc][(sc & 1) * 16];
+          float x[16];                                  // pre-activation (the bias came through the MMA)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(raw[cc][j]);
-          uint32_t hi[16], lo[16];
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(rw[j]);
+          uint32_t hi[8], lo[8];
           if (l < 3) {                                  // next layer's A operand: fp16 hi/lo planes in TMEM
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               hi[j] = pack_f16x2_rz_relu(x[2 * j], x[2 * j + 1]);
               // lo = x - hi (hi = x rounded toward zero, ReLU folded in: lo >= 0 wherever x > 0, and for x <= 0 the
               // second relu-conversion gives 0)
@@ -548,27 +560,46 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
             }
             if (RANGE) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) xmax = fmaxf(fmaxf(x[2 * j], x[2 * j + 1]), xmax);
+              for (int j = 0; j < 8; ++j) xmax = fmaxf(fmaxf(x[2 * j], x[2 * j + 1]), xmax);
             }
-            tmem_st16(t_lane + 128u + (uint32_t)(c0 >> 1), hi);
-            if (NPASS > 1) tmem_st16(t_lane + 192u + (uint32_t)(c0 >> 1), lo);
+            tmem_st8(t_lane + 128u + (uint32_t)(c0 >> 1), hi);
+            if (NPASS > 1) tmem_st8(t_lane + 192u + (uint32_t)(c0 >> 1), lo);
           } else {
             const float* w4 = cst + TC_C_W4 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o = fmaf(fmaxf(x[j], 0.f), w4[j], o);
+            for (int j = 0; j < 16; ++j) o = fmaf(fmaxf(x[j], 0.f), w4[j], o);
           }
-          if (SAVE) {                                   // saved for the backward as bf16 planes (ReLU folded into the cvt)
+          if (SAVE) {
+            // saved for the backward.  One-plane plan: the fp16 hi plane itself (x rounded toward zero, ReLU folded into
+            // the cvt -- no second conversion); two-plane plan: bf16 hi + lo planes.
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              hi[j] = pack_bf16x2_rn_relu(x[2 * j], x[2 * j + 1]);
-              mword[cc] |= tc_mask_bits(hi[j], j);
-              if (SAVE == 2)
+            for (int j = 0; j < 8; ++j) {
+              if (SAVE == 1) {
+                if (l == 3) hi[j] = pack_f16x2_rz_relu(x[2 * j], x[2 * j + 1]);
+#ifndef BH_EXP_NOMASK      // timing experiment: no relu bit masks (wrong gradients)
+                mword[cc] |= tc_mask_bits_f16(hi[j], j0 + j);
+#endif
+              } else {
+                hi[j] = pack_bf16x2_rn_relu(x[2 * j], x[2 * j + 1]);
+                mword[cc] |= tc_mask_bits(hi[j], j0 + j);
                 lo[j] = pack_bf16x2(fmaxf(x[2 * j], 0.f) - bf16_lo(hi[j]), fmaxf(x[2 * j + 1], 0.f) - bf16_hi(hi[j]));
+              }
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
+#ifdef BH_EXP_NOSAVESTG    // timing experiment: the activation images are not written (wrong gradients)
+              if (hi[4 * g] == 0x12345678u)
+#endif
+#if defined(BH_EXP_STCS)
+              __stcs(reinterpret_cast<uint4*>(act_img + sample_img_off(row, (c0 >> 3) + g)),
+                     make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]));
+#elif defined(BH_EXP_STWT)
+              __stwt(reinterpret_cast<uint4*>(act_img + sample_img_off(row, (c0 >> 3) + g)),
+                     make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]));
+#else
               *reinterpret_cast<uint4*>(act_img + sample_img_off(row, (c0 >> 3) + g)) =
                   make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+#endif
               if (SAVE == 2)
                 *reinterpret_cast<uint4*>(act_img + (size_t)v.n_pad * 1024u + sample_img_off(row, (c0 >> 3) + g)) =
                     make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
@@ -585,9 +616,10 @@ tc_fwd_body(uint8_t* smem, const PackedView& v, const FrameConsts& fc, const uin
           *reinterpret_cast<uint2*>(acts + (size_t)b * tc_acts_bytes_per_frame(v.n_pad, SAVE) + tc_mask_off(v.n_pad, SAVE) +
                                     tc_mask_word_off(tile, l, half, row)) = make_uint2(mword[0], mword[1]);
         BH_TIMING_END(t_ep)
-        if (l == 0 && has_next) {                       // the next tile's features, under the MMAs of layer 1 (and 2)
+        if (l < 2 && has_next) {                        // the next tile's features, under the MMAs of layers 1 and 2
           BH_TIMING_BEGIN
-          features(r + 1, n_valid, n_ray);
+          if (l == 0) features_a(r + 1, n_valid, n_ray);
+          else features_b(r + 1);
           BH_TIMING_END(t_ft)
         }
       }

@@ -48,20 +48,29 @@ struct PairLink {
 #else
 #define BH_DSTORE(p, v) (*reinterpret_cast<uint4*>(p) = (v))
 #endif
-// split two fp32 cotangents into packed bf16 hi / lo words and apply the relu mask m (0xffff per surviving half)
+// pack two fp32 cotangents and apply the relu mask m (0xffff per surviving half).  One-plane plan: ONE fp16 word (the
+// cotangents carry the launch-wide power-of-two scale, tc_grad_scale); two-plane plan: bf16 hi / lo words.
 template <int PL>
 __device__ __forceinline__ void delta_pack(uint32_t m, float a, float b, uint32_t& hi, uint32_t& lo) {
-  uint32_t p = pack_bf16x2(a, b);
-  hi = p & m;
-  if (PL == 2) lo = pack_bf16x2(a - bf16_lo(p), b - bf16_hi(p)) & m;
+  if (PL == 1) {
+    hi = pack_f16x2(a, b) & m;
+  } else {
+    uint32_t p = pack_bf16x2(a, b);
+    hi = p & m;
+    lo = pack_bf16x2(a - bf16_lo(p), b - bf16_hi(p)) & m;
+  }
 }
 
 // d loss / d o of every evaluated sample, once per backward, so that the dependent gathers (ray -> dI[ray]) are
 // off the dgrad chain:  dout = e(1-e) * sum_c dI[b,c,ray] * w[c,i]   (sigmoid', network.py:230; kgeo.py:621).
 // In place over e when the caller owns that buffer (dout == e is allowed: one thread reads and writes an element).
+// Also reduces max|dout| of the launch into *dout_max (uint32 bits of a non-negative float order like the float; zeroed
+// by the launcher): the scale of the fp16 cotangents (tc_grad_scale).
 __global__ void __launch_bounds__(256)
-tc_dout_kernel(PackedView v, const float* __restrict__ d_images, const float* e, int Bt, float* dout) {
+tc_dout_kernel(PackedView v, const float* __restrict__ d_images, const float* e, int Bt, float* dout,
+               uint32_t* __restrict__ dout_max) {
   const size_t n = (size_t)Bt * v.n_pad;
+  float mx = 0.f;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(idx / v.n_pad), i = (int)(idx - (size_t)b * v.n_pad);
     const int ray = v.ray[i];
@@ -69,8 +78,13 @@ tc_dout_kernel(PackedView v, const float* __restrict__ d_images, const float* e,
     if (ray >= 0)
       for (int c = 0; c < v.S; ++c) g += d_images[((size_t)b * v.S + c) * v.P + ray] * v.w[(size_t)c * v.n_pad + i];
     const float ev = e[idx];
-    dout[idx] = g * ev * (1.f - ev);
+    const float d = g * ev * (1.f - ev);
+    dout[idx] = d;
+    mx = fmaxf(mx, fabsf(d));
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(dout_max, __float_as_uint(mx));
 }
 
 template <int PL, bool FUSED, bool WIDE>
@@ -99,6 +113,10 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
   }
   if (warp == kDMmaWarp) tmem_alloc(tmem_base_s, 512);
   if (tid < 128) w4s[tid] = ((const float*)(ws + TC_WS_CONST))[TC_C_W4 + tid];
+  // one-plane plan: launch-wide power-of-two scale of the fp16 cotangents
+  float ginv = 1.f;
+  const float gscale = PL == 1 ? tc_grad_scale(((const uint32_t*)(ws + TC_WS_CONST))[TC_C_DOUTMAX], ginv) : 1.f;
+  (void)ginv;
   tc_fence_before_sync();
   __syncthreads();
   if (FUSED) cluster_sync_all();          // the partner's barriers exist before anyone arrives on them
@@ -107,16 +125,24 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 
   if (warp == kDMmaWarp + 1) {
     if (lane == 0) {      // resident weights: layers 1..3 [hi|lo] images, one shot
-      mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
-      const uint8_t* src = ws + TC_WS_WB + 16384u;
-      bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
-      bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
-      bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
+      if (PL == 1) {      // the forward's fp16 images (layer 3 = its 128-row hidden part): 3 x 64 KB, contiguous
+        mbar_expect_tx(&bars[DB_WFULL], 196608u);
+        const uint8_t* src = ws + TC_WS_W + 16384u;
+        bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
+        bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
+        bulk_g2s(wsm + 131072u, src + 131072u, 65536u, &bars[DB_WFULL]);
+      } else {            // bf16 images of the two-plane plan
+        mbar_expect_tx(&bars[DB_WFULL], DW_BYTES);
+        const uint8_t* src = ws + TC_WS_WB + 16384u;
+        bulk_g2s(wsm, src, 65536u, &bars[DB_WFULL]);
+        bulk_g2s(wsm + 65536u, src + 65536u, 65536u, &bars[DB_WFULL]);
+        bulk_g2s(wsm + 131072u, src + 131072u, 81920u, &bars[DB_WFULL]);
+      }
     }
     __syncwarp();
   } else if (warp == kDMmaWarp) {
     {   // whole warp runs the loop; elect.sync inside the issue wrappers picks the issuing lane
-      const uint32_t idesc = make_idesc(128, 128, 0, 0);      // A from TMEM, B K-major
+      const uint32_t idesc = PL == 1 ? make_idesc_f16(128, 128, 0, 0) : make_idesc(128, 128, 0, 0);   // A from TMEM, B K-major
       uint32_t a_phase[2] = {0u, 0u};
       BH_TIMING_T0 BH_TIMING_DECL(t_wa) BH_TIMING_DECL(t_is)
       bool ok = wait(&bars[DB_WFULL], 0, ab);
@@ -124,8 +150,9 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         int T0 = (r * ncta + cta) * 2;
         if (T0 >= NT) break;
         for (int l = 3; l >= 1 && ok; --l) {
-          const uint32_t wl = smem_u32(wsm) + tc_stage_off(l) - 16384u;
-          const uint32_t plane = tc_plane_bytes(l), cs = (tc_layer_K(l) / 8u) * 128u;
+          // one-plane plan: fp16 images of 128 rows each; two-plane plan: bf16 images, layer 3 with its 160 rows
+          const uint32_t wl = smem_u32(wsm) + (PL == 1 ? (uint32_t)(l - 1) * 65536u : tc_stage_off(l) - 16384u);
+          const uint32_t plane = PL == 1 ? 32768u : tc_plane_bytes(l), cs = PL == 1 ? 2048u : (tc_layer_K(l) / 8u) * 128u;
           for (int s = 0; s < 2; ++s) {
             if (T0 + s >= NT) continue;
             BH_TIMING_BEGIN
@@ -248,13 +275,14 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         }
         uint32_t d[16], dl[16];
         const uint32_t mw = mk[s][3];
+        const float douts = dout[s] * gscale;
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
           const uint32_t off = sample_img_off(row, cgrp * 4 + gq);
           const float* w4 = w4s + (cgrp * 4 + gq) * 8;
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
-            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), dout[s] * w4[2 * jj], dout[s] * w4[2 * jj + 1], d[4 * gq + jj], dl[4 * gq + jj]);
+            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), douts * w4[2 * jj], douts * w4[2 * jj + 1], d[4 * gq + jj], dl[4 * gq + jj]);
           BH_DSTORE(del_tile[s] + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
           if (PL == 2)
             *reinterpret_cast<uint4*>(del_tile[s] + pstride + 3 * dls + off) =
@@ -417,6 +445,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         *reinterpret_cast<uint4*>(aux + sample_img_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
       // delta_3[j] = dout * W4[j] * (h3[j] > 0)
+      const float douts = dout * gscale;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t d[16], dl[16];
@@ -425,10 +454,10 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           const uint32_t off = sample_img_off(row, cg0 + 4 * cc + gq);
           const uint32_t mw = cc ? mk[3].y : mk[3].x;
           const float* w4 = w4s + (cg0 + 4 * cc + gq) * 8;
-          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), dout * w4[0], dout * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
-          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), dout * w4[2], dout * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
-          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), dout * w4[4], dout * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
-          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 3), dout * w4[6], dout * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 0), douts * w4[0], douts * w4[1], d[4 * gq + 0], dl[4 * gq + 0]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 1), douts * w4[2], douts * w4[3], d[4 * gq + 1], dl[4 * gq + 1]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 2), douts * w4[4], douts * w4[5], d[4 * gq + 2], dl[4 * gq + 2]);
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + 3), douts * w4[6], douts * w4[7], d[4 * gq + 3], dl[4 * gq + 3]);
           BH_DSTORE(del_tile + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
           if (PL == 2)
             *reinterpret_cast<uint4*>(del_tile + pstride + 3 * dls + off) =
@@ -578,6 +607,9 @@ __device__ __forceinline__ void
 wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, int n_pad, int Bt,
            const uint8_t* __restrict__ acts, const uint8_t* __restrict__ deltas, float* __restrict__ d_params,
            int* __restrict__ status) {
+  // status = first bytes of the tcgen05 workspace: the fp32 constants (and the cotangent scale) sit TC_WS_CONST behind it
+  float ginv = 1.f;
+  if (PL == 1) tc_grad_scale(((const uint32_t*)((const uint8_t*)status + TC_WS_CONST))[TC_C_DOUTMAX], ginv);
   static_assert(!(FUSED && PL == 2), "the fused pair runs the one-plane plan");
   constexpr int kWStages = WCfg<PL>::kWStages;
   constexpr uint32_t W_SM_BARS = WCfg<PL>::SM_BARS;
@@ -672,8 +704,10 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, 
   } else if (warp == 4) {
     // ===================== MMA issuer (whole warp, elect.sync inside the issue wrappers) =====================
     {
-      const uint32_t id160 = make_idesc(128, 160, 1, 1), id144 = make_idesc(128, 144, 1, 1),
-                     id32 = make_idesc(128, 32, 1, 1), id16 = make_idesc(128, 16, 1, 1);
+      const uint32_t id160 = PL == 1 ? make_idesc_f16(128, 160, 1, 1) : make_idesc(128, 160, 1, 1),
+                     id144 = PL == 1 ? make_idesc_f16(128, 144, 1, 1) : make_idesc(128, 144, 1, 1),
+                     id32 = PL == 1 ? make_idesc_f16(128, 32, 1, 1) : make_idesc(128, 32, 1, 1),
+                     id16 = PL == 1 ? make_idesc_f16(128, 16, 1, 1) : make_idesc(128, 16, 1, 1);
       uint32_t cnt = 0;
       bool ok = true;
       uint32_t later_tile = 0;               // 0 for the CTA's first tile: accumulators start from zero
@@ -762,10 +796,17 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, 
             const uint32_t dw = *reinterpret_cast<const uint32_t*>(aux + rg * TC_IMG_RS);     // row rg*8+rp: (hi, lo) of dout
             const float dout = bf16_lo(dw) + bf16_hi(dw);
             const uint4 hv = *reinterpret_cast<const uint4*>(img + rg * TC_IMG_RS);
-            w4acc[0] = fmaf(bf16_lo(hv.x), dout, w4acc[0]); w4acc[1] = fmaf(bf16_hi(hv.x), dout, w4acc[1]);
-            w4acc[2] = fmaf(bf16_lo(hv.y), dout, w4acc[2]); w4acc[3] = fmaf(bf16_hi(hv.y), dout, w4acc[3]);
-            w4acc[4] = fmaf(bf16_lo(hv.z), dout, w4acc[4]); w4acc[5] = fmaf(bf16_hi(hv.z), dout, w4acc[5]);
-            w4acc[6] = fmaf(bf16_lo(hv.w), dout, w4acc[6]); w4acc[7] = fmaf(bf16_hi(hv.w), dout, w4acc[7]);
+            if (PL == 1) {        // h3 saved as fp16
+              w4acc[0] = fmaf(f16_lo(hv.x), dout, w4acc[0]); w4acc[1] = fmaf(f16_hi(hv.x), dout, w4acc[1]);
+              w4acc[2] = fmaf(f16_lo(hv.y), dout, w4acc[2]); w4acc[3] = fmaf(f16_hi(hv.y), dout, w4acc[3]);
+              w4acc[4] = fmaf(f16_lo(hv.z), dout, w4acc[4]); w4acc[5] = fmaf(f16_hi(hv.z), dout, w4acc[5]);
+              w4acc[6] = fmaf(f16_lo(hv.w), dout, w4acc[6]); w4acc[7] = fmaf(f16_hi(hv.w), dout, w4acc[7]);
+            } else {
+              w4acc[0] = fmaf(bf16_lo(hv.x), dout, w4acc[0]); w4acc[1] = fmaf(bf16_hi(hv.x), dout, w4acc[1]);
+              w4acc[2] = fmaf(bf16_lo(hv.y), dout, w4acc[2]); w4acc[3] = fmaf(bf16_hi(hv.y), dout, w4acc[3]);
+              w4acc[4] = fmaf(bf16_lo(hv.z), dout, w4acc[4]); w4acc[5] = fmaf(bf16_hi(hv.z), dout, w4acc[5]);
+              w4acc[6] = fmaf(bf16_lo(hv.w), dout, w4acc[6]); w4acc[7] = fmaf(bf16_hi(hv.w), dout, w4acc[7]);
+            }
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");      // all four warps are done with the stage
           if (tid == 0) mbar_arrive(&bars[WB_EMPTY + st]);
@@ -779,6 +820,7 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, 
         vsum += __shfl_xor_sync(0xffffffffu, vsum, 1);
         vsum += __shfl_xor_sync(0xffffffffu, vsum, 2);
         vsum += __shfl_xor_sync(0xffffffffu, vsum, 4);
+        if (PL == 1) vsum *= TC_RZ_UNBIAS;                           // h3 is rz-truncated too (see the flush below)
         if (rp == 0 && vsum != 0.f) atomicAdd(d_params + OFF_W4 + cg * 8 + c, vsum);
         if (rp == 0 && !(fabsf(vsum) <= 3.0e38f)) abort_s[1] = 1;
       }
@@ -797,7 +839,12 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, 
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const uint32_t c = c0 + (uint32_t)jj;
-          const float val = __uint_as_float(raw[jj]);
+          // undo the cotangent scale (power of two: exact).  One-plane plan: the saved h0..h2 are the forward's fp16 hi
+          // plane, rounded TOWARD ZERO -- every product with them is low by the mean relative truncation,
+          // 2^-11 * (1/2)/ln 2 = 3.52e-4 for mantissas spread log-uniformly over a binade (measured on cfg1 / cfg2:
+          // 3.5e-4 .. 3.6e-4 of dW1..dW3, profiles/r2_grad_ab_fp16.log); the flush removes that bias
+          const bool from_h = PL == 1 && (c < ACC_W3F || (c >= ACC_W2 && c < ACC_B2) || (c >= ACC_W1 && c < ACC_B1));
+          const float val = __uint_as_float(raw[jj]) * (from_h ? ginv * TC_RZ_UNBIAS : ginv);
           int dst = -1;
           if (c < ACC_W3F) dst = OFF_W3 + (int)c * 128 + n;
           else if (c < ACC_W2) { int kf = (int)(c - ACC_W3F); dst = kf < BH_NF ? OFF_W3 + (128 + kf) * 128 + n : (kf == TC_ONES_COL ? OFF_B3 + n : -1); }
@@ -902,7 +949,9 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
     BhProfScope ps(BH_CAT_HEADS, 1, st);
     size_t n = (size_t)Bt * v.n_pad;
     int grid = (int)((n + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
-    tc_dout_kernel<<<grid, 256, 0, st>>>(v, d_images, e_saved, Bt, dout);
+    uint32_t* dout_max = (uint32_t*)((uint8_t*)ws + TC_WS_CONST) + TC_C_DOUTMAX;
+    BH_CHECK_CUDA(cudaMemsetAsync(dout_max, 0, sizeof(uint32_t), st));
+    tc_dout_kernel<<<grid, 256, 0, st>>>(v, d_images, e_saved, Bt, dout, dout_max);
     BH_CHECK_CUDA(cudaGetLastError());
   }
   if (PL == 1 && bwd_fused_enabled()) {

@@ -1,6 +1,7 @@
 // Shared pieces of the tcgen05 kernel family (render_tc_fwd.cu, render_tc_bwd.cu): global workspace
 // layout, operand-image geometry, abortable mbarrier waits, bulk global->shared copies.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -57,6 +58,7 @@ __host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { 
 #define TC_C_W4 512
 #define TC_C_B4 640
 #define TC_C_RANGE 641                   // != 0: the weights allow |h| > 65504, the forward epilogue tracks the range
+#define TC_C_DOUTMAX 700                 // uint32 bits of max |d loss / d o| of the current backward launch (tc_dout_kernel)
 
 // Optional cycle accounting (-DBH_TC_TIMING): block 0 writes, per role, the cycles spent waiting vs working into
 // the workspace status words [8..20) (two int32 per counter).  Compiled out by default.
@@ -117,6 +119,23 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
+// ---- cotangent scale of the one-plane backward (fp16 operands) ----
+// The saved activations of the one-plane plan are the forward's fp16 hi plane, so the cotangents must be fp16 too
+// (tcgen05.mma takes one 16-bit format per instruction).  Their range is set by d loss/d o, which spans many decades
+// across samples: all of them are multiplied by ONE power of two s, chosen from max|dout| of the launch so that
+// max|dout| * s lies in [2, 4) -- the chain is linear, so s rides through every layer and the wgrad flush multiplies by
+// 1/s (exact).  Contributions below 2^-26 of the largest flush to zero, above 2^-16 of it they keep all 11 bits; three
+// layers of worst-case growth (row sums of |W|) stay below 65504 for any weights with row sums under ~25 -- beyond that
+// the non-finite gradient is flagged (status word 4), not hidden.
+__device__ __forceinline__ float tc_grad_scale(uint32_t max_bits, float& inv) {
+  const int e = (int)((max_bits >> 23) & 0xFFu) - 127;          // floor(log2 max|dout|)
+  if (max_bits == 0u || e < -100 || e > 100) { inv = 1.f; return 1.f; }
+  inv = __uint_as_float((uint32_t)(127 + e - 1) << 23);
+  return __uint_as_float((uint32_t)(127 + 1 - e) << 23);
+}
+
+#define TC_RZ_UNBIAS 1.000352215f       // 1 + 2^-11 * 0.5 / ln 2: mean relative truncation of cvt.rz to fp16
+
 // ---- ReLU bit masks ----
 // One 32-bit word covers 32 consecutive columns = 16 packed bf16 pairs.  Pair j (columns 2j, 2j+1) keeps its two bits
 // at positions p and p + 16 with p = 8*(j&1) + 7 - (j>>1): after a left shift by (j>>1) they are the sign bits of
@@ -128,6 +147,10 @@ __device__ __forceinline__ constexpr uint32_t tc_mask_pair_bits(int j) {
 // bits of pair j from a packed bf16 pair of (relu'd) activations
 __device__ __forceinline__ uint32_t tc_mask_bits(uint32_t h2, int j) {
   return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&h2), __float2bfloat162_rn(0.f)) & tc_mask_pair_bits(j);
+}
+// same from a packed fp16 pair (one-plane plan: the saved activation IS the forward's fp16 hi plane)
+__device__ __forceinline__ uint32_t tc_mask_bits_f16(uint32_t h2, int j) {
+  return __hgt2_mask(*reinterpret_cast<const __half2*>(&h2), __float2half2_rn(0.f)) & tc_mask_pair_bits(j);
 }
 // 0xffff per half of pair j where the activation was positive
 __device__ __forceinline__ uint32_t tc_mask_expand(uint32_t word, int j) {

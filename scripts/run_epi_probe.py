@@ -42,3 +42,20 @@ for i in sorted(NAMES):
     c = cyc.double().mean().item()
     per_smsp = c / (iters * n * 4)      # 4 warps per SMSP issue n instructions per iteration each
     print('%-90s %10.3f %10.3f' % (NAMES[i], per_smsp, 1.0 / per_smsp), flush=True)
+
+# ---- stand-alone replica of the forward layer epilogue: cycles per tile-layer pair (both slots in parallel) ----
+lib.epi_full_run.restype = C.c_int
+lib.epi_full_run.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+gbuf = torch.empty(4 << 30, dtype=torch.uint8, device='cuda')
+sink = torch.zeros(148 * 512, dtype=torch.int32, device='cuda')
+FL = {63: 'all (LDTM, hi+lo split, STTM, masks, STG)', 47: 'no STG', 55: 'no masks', 39: 'no masks, no STG', 59: 'no STTM',
+      62: 'no LDTM', 1: 'LDTM only', 5: 'LDTM + STTM (no conversion)', 34: 'split only (hi + lo)', 31: 'no lo plane',
+      17: 'LDTM + STG', 16: 'STG only', 42: 'split + masks'}
+print('\n%-60s %12s' % ('epilogue replica: parts', 'cycles per tile-layer pair'))
+it2 = 400
+for f, name in FL.items():
+    for _ in range(2):
+        rc = lib.epi_full_run(f, gbuf.data_ptr(), gbuf.numel(), it2, cyc.data_ptr(), sink.data_ptr(), st)
+        torch.cuda.synchronize()
+    assert rc == 0, rc
+    print('%-60s %12.0f' % (name, cyc.double().mean().item() / it2), flush=True)

@@ -9,12 +9,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
-out = os.path.join(ge.LIBDIR, 'libbhnerf_b200_timing.so')
+flags = [a for a in sys.argv[1:] if a.startswith('-D')]
+tag = ''.join(c if c.isalnum() else '_' for c in ''.join(flags))
+out = os.path.join(ge.LIBDIR, 'libbhnerf_b200_timing%s.so' % tag)
 srcs = [os.path.join(ge.CSRC, f) for f in ge.LIB_SOURCES]
-if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
-    subprocess.check_call(['/usr/local/cuda/bin/nvcc'] + ge.NVCC_FLAGS + ['-DBH_TC_TIMING', '-o', out] + srcs)
-if len(sys.argv) > 1 and sys.argv[1] == 'build':
+hdrs = [os.path.join(ge.CSRC, f) for f in os.listdir(ge.CSRC) if f.endswith('.cuh')]
+if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs + hdrs):
+    subprocess.check_call(['/usr/local/cuda/bin/nvcc'] + ge.NVCC_FLAGS + ['-DBH_TC_TIMING'] + flags + ['-o', out] + srcs)
+if 'build' in sys.argv:
     sys.exit(0)
+print('variant:', tag or 'base')
 os.environ['BHNERF_B200_LIB'] = out
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

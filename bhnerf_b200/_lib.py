@@ -57,6 +57,13 @@ SIGNATURES = {
                                + [_vp] * 7),
     'bhnerf_adam_step_dev': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _f32, _f32, _i32, _f32, _f32, _f32, _f32, _vp, _vp]),
     'bhnerf_workspace_status': (C.c_int, [_vp, C.POINTER(C.c_int32), _vp]),
+    'bhnerf_comm_unique_id': (C.c_int, [_vp]),
+    'bhnerf_comm_init': (C.c_int, [_i32, _i32, _vp, C.POINTER(C.c_void_p)]),
+    'bhnerf_comm_destroy': (C.c_int, [_vp]),
+    'bhnerf_allreduce_mean': (C.c_int, [_vp, C.c_int64, _vp, _vp]),
+    'bhnerf_allreduce_sum': (C.c_int, [_vp, C.c_int64, _vp, _vp]),
+    'bhnerf_lightcurve': (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    'bhnerf_loss_lightcurve': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp, _vp]),
     'bhnerf_add_inplace': (C.c_int, [_vp, _vp, _i32, _vp]),
     'bhnerf_adam_step': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _i32, _f32, _f32, _f32, _f32,
                                    _vp, _vp]),

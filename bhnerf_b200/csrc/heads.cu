@@ -81,6 +81,43 @@ __global__ void loss_lc_kernel(const float* __restrict__ I, const float* __restr
   if (threadIdx.x == 0) atomicAdd(loss, scale * r * r);
 }
 
+// the two halves of the 'lc' head, for ray-sharded ranks (partial lightcurves are all-reduced in between)
+__global__ void lightcurve_kernel(const float* __restrict__ I, int P, float* __restrict__ lc) {
+  __shared__ float sh[32];
+  const float* row = I + (size_t)blockIdx.x * P;
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) acc += row[p];
+  float tot = block_reduce_sum(acc, sh);
+  if (threadIdx.x == 0) lc[blockIdx.x] = tot;
+}
+__global__ void loss_from_lightcurve_kernel(const float* __restrict__ lc, const float* __restrict__ t,
+                                            const float* __restrict__ sg, const float* __restrict__ off, float scale,
+                                            int P, float* __restrict__ loss, float* __restrict__ dI) {
+  int bs = blockIdx.x;
+  float r = (lc[bs] - t[bs] - off[bs]) / sg[bs];
+  float d = 2.f * scale * r / sg[bs];
+  for (int p = threadIdx.x; p < P; p += blockDim.x) dI[(size_t)bs * P + p] = d;
+  if (threadIdx.x == 0) atomicAdd(loss, scale * r * r);
+}
+extern "C" int bhnerf_lightcurve(const float* images, int32_t Bt, int32_t S, int32_t P, float* lc, void* stream) {
+  BH_REQUIRE(images && lc && Bt > 0 && S > 0 && P > 0, "lightcurve: bad argument");
+  BhProfScope ps(BH_CAT_HEADS, 1, (cudaStream_t)stream);
+  lightcurve_kernel<<<Bt * S, 256, 0, (cudaStream_t)stream>>>(images, P, lc);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int bhnerf_loss_lightcurve(const float* lc, const float* target, const float* sigma, const float* offset,
+                                      float loss_scale, int32_t Bt, int32_t S, int32_t P, float* loss, float* d_images,
+                                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BH_REQUIRE(lc && target && sigma && offset && loss && d_images && Bt > 0 && S > 0 && P > 0, "loss_lightcurve: bad argument");
+  BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  BhProfScope ps(BH_CAT_HEADS, 1, st);
+  loss_from_lightcurve_kernel<<<Bt * S, 256, 0, st>>>(lc, target, sigma, offset, loss_scale, P, loss, d_images);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // accumulates into *loss (caller zeroes it)
 int bh_loss_image_accum(const float* images, const float* target, const float* sigma, const float* offset,
                         float loss_scale, int kind, int Bt, int S, int P, float* loss, float* d_images,

@@ -27,6 +27,9 @@ namespace {
 // =====================================================================================================
 // dgrad chain
 // =====================================================================================================
+#ifndef BH_DGRAD_PASSES
+#define BH_DGRAD_PASSES 2     // products per layer of the one-plane chain: d*W_hi (+ d*W_lo)
+#endif
 constexpr int kDThreads = 576;           // 16 epilogue warps + MMA issuer + weight loader
 constexpr int kDMmaWarp = 16;
 constexpr uint32_t DW_BYTES = TC_W_BYTES - 16384u;                 // stages of layers 1..3, contiguous in ws
@@ -169,7 +172,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
               const uint32_t b_hi = desc_hi(TC_IMG_RS), b_lo0 = desc_lo(wl, cs), b_lo1 = desc_lo(wl + plane, cs);
               const uint32_t kstep = (2u * cs) >> 4;
 #pragma unroll
-              for (int pp = 0; pp < (PL == 2 ? 3 : 2); ++pp)
+              for (int pp = 0; pp < (PL == 2 ? 3 : BH_DGRAD_PASSES); ++pp)
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                   mma_ts_raw(td, ta + (pp == 2 ? 64u : 0u) + (uint32_t)ks * 8u, (pp == 1 ? b_lo1 : b_lo0) + (uint32_t)ks * kstep,

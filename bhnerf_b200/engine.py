@@ -391,3 +391,86 @@ def step_guard(device, impl=None):
     """Workspace to pass as `guard` to the Adam update that follows a render step of kernel family `impl` (tcgen05 only:
     the fp32 SIMT family keeps weights, not flags, at the head of its scratch)."""
     return current_workspace(device) if resolve_impl(impl) == IMPL_TC else None
+
+
+# ------------------------------------------------------------------------------------------------
+# gradient exchange below the C ABI (bhnerf_allreduce_mean / _sum: NCCL on the kernel stream)
+# ------------------------------------------------------------------------------------------------
+_comms = {}
+
+
+def _dist_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def comm(device=None):
+    """This rank's NCCL communicator inside libbhnerf_b200 (None with a single rank).  Created collectively on first
+    use: rank 0 draws the unique id (bhnerf_comm_unique_id), torch.distributed -- the host-side plumbing -- broadcasts its
+    128 bytes, every rank calls bhnerf_comm_init.  Afterwards the data path never touches torch.distributed."""
+    dist, rank, world = _dist_world()
+    if dist is None:
+        return None
+    key = torch.cuda.current_device() if device is None else _dev_key(torch.device(device))
+    hit = _comms.get(key)
+    if hit is not None:
+        return hit
+    lib = _lib.load()
+    idbuf = C.create_string_buffer(128)
+    if rank == 0:
+        check(lib.bhnerf_comm_unique_id(idbuf))
+    box = [idbuf.raw if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    idbuf = C.create_string_buffer(box[0], 128)
+    handle = C.c_void_p()
+    with torch.cuda.device(key):
+        check(lib.bhnerf_comm_init(rank, world, idbuf, C.byref(handle)))
+    _comms[key] = handle
+    return handle
+
+
+def allreduce_mean(t):
+    """In-place mean over ranks of a float32 device tensor (jax.lax.pmean, network.py:620).  C ABI: bhnerf_allreduce_mean."""
+    c = comm(t.device)
+    if c is None:
+        return t
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    with torch.cuda.device(t.device):
+        check(_lib.load().bhnerf_allreduce_mean(_ptr(t), t.numel(), c, _stream()))
+    return t
+
+
+def allreduce_sum(t):
+    """In-place sum over ranks (float32, or complex64 seen as interleaved float32).  C ABI: bhnerf_allreduce_sum."""
+    c = comm(t.device)
+    if c is None:
+        return t
+    assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.complex64)
+    n = t.numel() * (2 if t.dtype == torch.complex64 else 1)
+    with torch.cuda.device(t.device):
+        check(_lib.load().bhnerf_allreduce_sum(_ptr(t), n, c, _stream()))
+    return t
+
+
+def lightcurve(images):
+    """lc [Bt,S] = sum over rays of images [Bt,S,P].  C ABI: bhnerf_lightcurve."""
+    Bt, S, P = images.shape
+    lc = torch.empty((Bt, S), dtype=torch.float32, device=images.device)
+    with torch.cuda.device(images.device):
+        check(_lib.load().bhnerf_lightcurve(_ptr(images), Bt, S, P, _ptr(lc), _stream()))
+    return lc
+
+
+def loss_lightcurve(lc, target, sigma, offset, scale, P):
+    """(loss[1], d_images [Bt,S,P]) of the 'lc' head from (all-reduced) lightcurves.  C ABI: bhnerf_loss_lightcurve."""
+    dev = lc.device
+    Bt, S = lc.shape
+    target, sigma, offset = [_dev_f32(a, dev).reshape(Bt, S) for a in (target, sigma, offset)]
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dI = torch.empty((Bt, S, P), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().bhnerf_loss_lightcurve(_ptr(lc), _ptr(target), _ptr(sigma), _ptr(offset), float(scale), Bt, S, P,
+                                                 _ptr(loss), _ptr(dI), _stream()))
+    return loss, dI

@@ -259,21 +259,50 @@ class GRID_Predictor:
 _scene_cache = OrderedDict()
 
 
-def _scene_for(predictor, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units, device=None):
+SCENE_CACHE_SIZE = int(os.environ.get('BHNERF_SCENE_CACHE', '64'))   # >= the number of sub-pixel raytracing_args sets
+
+
+def _ray_block(a, ray_shard, lead):
+    """Rays [r*P/R, (r+1)*P/R) of an array whose axes after the first `lead` are (A, B, G) (ray-major flattening of A x B)."""
+    rank, world = ray_shard
+    a = np.asarray(a)
+    shp = a.shape
+    P = int(np.prod(shp[lead:-1]))
+    if P % world:
+        raise ValueError('%d rays are not divisible by %d ranks' % (P, world))
+    per = P // world
+    flat = a.reshape(shp[:lead] + (P, shp[-1]))
+    return np.ascontiguousarray(flat[..., rank * per:(rank + 1) * per, :]).reshape(shp[:lead] + (per, 1, shp[-1]))
+
+
+def _scene_for(predictor, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units, device=None,
+               ray_shard=None):
+    """Prepacked scene of the raytracing args, cached on the identity of the arrays (they are kept alive by the cache; an
+    in-place mutation of a cached array is NOT seen -- pass a fresh array).  ray_shard = (rank, world): the scene of this
+    rank's contiguous block of rays only (image_shape (P/world, 1))."""
     tsv = float(utils.time_value(t_start_obs, t_units))
     key = (id(coords), id(Omega), id(J) if not np.isscalar(J) else ('scalar', float(J)), id(g), id(dtau), id(Sigma),
            id(t_geos), tsv, float(t_injection), predictor.scale, predictor.rmin, predictor.rmax, predictor.z_width,
-           str(t_units), str(device))
+           str(t_units), str(device), ray_shard)
     hit = _scene_cache.get(key)
     if hit is not None:
         _scene_cache.move_to_end(key)
         return hit[0]
-    scene = engine.PackedScene(coords, Omega, J, g, dtau, Sigma, t_geos, tsv, float(t_injection), predictor.scale,
+    if ray_shard is None:
+        parts = (coords, Omega, J, g, dtau, Sigma, t_geos)
+    else:
+        parts = (_ray_block(coords, ray_shard, 1), _ray_block(Omega, ray_shard, 0),
+                 J if np.isscalar(J) else _ray_block(J, ray_shard, 1), _ray_block(g, ray_shard, 0),
+                 _ray_block(dtau, ray_shard, 0), _ray_block(Sigma, ray_shard, 0), _ray_block(t_geos, ray_shard, 0))
+    c_, Om_, J_, g_, dt_, Sg_, tg_ = parts
+    scene = engine.PackedScene(c_, Om_, J_, g_, dt_, Sg_, tg_, tsv, float(t_injection), predictor.scale,
                                predictor.rmin, predictor.rmax, predictor.z_width, constants.GM_c3(t_units=t_units),
                                device=device)
+    if ray_shard is not None:
+        scene.full_image_shape = tuple(np.shape(Omega)[:-1])
     # keep the source arrays alive so the id()-based key stays valid
     _scene_cache[key] = (scene, (coords, Omega, J, g, dtau, Sigma, t_geos))
-    while len(_scene_cache) > 8:
+    while len(_scene_cache) > SCENE_CACHE_SIZE:
         _scene_cache.popitem(last=False)
     return scene
 
@@ -396,14 +425,18 @@ def _dist():
     return None
 
 
-def _pmean_and_apply(state, grads, update=True, guard=None):
-    """jax.lax.pmean(grads,'batch') + state.apply_gradients (network.py:620-621): all-reduce SUM over ranks,
-    the 1/ndev is folded into the Adam kernel's grad_scale."""
+def _pmean_and_apply(state, grads, update=True, guard=None, reduce='mean'):
+    """jax.lax.pmean(grads,'batch') + state.apply_gradients (network.py:620-621).  On the GPU the exchange is the C ABI's
+    bhnerf_allreduce_mean (NCCL on the kernel stream); `reduce='sum'` is the ray-sharded step, whose per-rank gradients are
+    partial sums of ONE device's gradient.  (CPU tensors -- the gloo tests of the host logic -- go through torch.distributed.)"""
     dist = _dist()
     scale = 1.0
     if dist is not None:
-        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
-        scale = 1.0 / dist.get_world_size()
+        if grads.is_cuda:
+            (engine.allreduce_mean if reduce == 'mean' else engine.allreduce_sum)(grads)
+        else:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+            scale = 1.0 / dist.get_world_size() if reduce == 'mean' else 1.0
     if update:
         if guard is not None:
             state.apply_gradients(grads, grad_scale=scale, guard=guard)
@@ -448,9 +481,13 @@ class _GraphedImageStep:
         self.state, self.scene = state, scene          # keep the captured buffers alive
         lib = engine._lib.load()
 
+        if _dist() is not None:
+            engine.comm(dev)                           # collective: created before the capture, on every rank
+
         def body():
             engine.train_step_image(scene, state.flat, self.tf, self.tgt, self.sig, self.off, float(scale), kind, impl,
                                     out=self.out)
+            engine.allreduce_mean(self.out[2])         # jax.lax.pmean (no-op with one rank); NCCL is graph-capturable
             engine.check(lib.bhnerf_adam_step_dev(engine._ptr(state.flat), engine._ptr(self.out[2]), engine._ptr(state.mu),
                                                   engine._ptr(state.nu), state.flat.numel(), engine._ptr(self.count),
                                                   state.lr_init, state.lr_final, state.num_iters, 0.9, 0.999, 1e-8, 1.0,
@@ -514,14 +551,64 @@ def _graphed_image_step(state, scene, Bt, kind, scale, impl):
     return hit
 
 
-def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, coords, Omega, J, g, dtau, Sigma,
-                        t_start_obs, t_geos, t_injection, scale, impl=None):
-    """bhnerf/network.py:566-622: value_and_grad(loss_fn_image) -> pmean -> apply_gradients.
-    Returns (loss, state, images)."""
+def _gather_rays(images_r, scene_r, J):
+    """(Bt,S,P/R) of every rank -> full images shaped like image_plane_prediction's (host-side plumbing, off the data path)."""
+    import torch.distributed as dist
+    outs = [torch.empty_like(images_r) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, images_r.contiguous())
+    full = torch.cat(outs, dim=2)
+    Bt, S = full.shape[:2]
+    shp = scene_r.full_image_shape
+    if not scene_r.polarized:
+        return full.reshape((Bt,) + shp)
+    out = full.reshape((Bt, S) + shp)
+    return out.squeeze() if (Bt == 1 or S == 1) else out
+
+
+def _ray_sharded_image_step(state, t_units, dtype, target, sigma, offset, t_frames, rt_args, scale, impl, ray_shard,
+                            update):
+    """Ray sharding for batches with fewer frames than ranks -- the reference cannot run those at all
+    (optimization.py:39, :360-362).  Every rank renders ALL frames of the batch for its contiguous block of P/world rays;
+    'full' needs no exchange before the loss, 'lc' all-reduces the (Bt,S) partial lightcurves BEFORE the loss
+    non-linearity; the per-rank gradients are partial sums, so they are all-reduced with SUM: the step equals ONE device's
+    step on the whole batch."""
+    if dtype not in ('full', 'lc'):
+        raise AttributeError('image dtype ({}) not supported'.format(dtype))
     pred = state.predictor
+    rank, world = ray_shard
+    scene = _scene_for(pred, *rt_args, t_units, device=state.flat.device, ray_shard=ray_shard)
+    tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
+                         scene.device).reshape(-1)
+    Bt, S, Pr = tf.numel(), scene.S, scene.P
+    images, e, acts = pred._render_fwd(scene, state.flat, tf, impl, save_acts=update)
+    if dtype == 'full':
+        def own(a):
+            a = engine._dev_f32(a, scene.device).reshape(Bt, S, -1)
+            return a[:, :, rank * Pr:(rank + 1) * Pr].contiguous()
+        loss, dI = engine.loss_image(images, own(target), own(sigma), own(offset), float(scale), 'full')
+        engine.allreduce_sum(loss)
+    else:
+        lc = engine.allreduce_sum(engine.lightcurve(images))
+        loss, dI = engine.loss_lightcurve(lc, target, sigma, offset, float(scale), Pr)
+    if update:
+        grads = pred._render_bwd(scene, state.flat, tf, dI, e, acts, impl)
+        guard = engine.step_guard(scene.device, impl) if isinstance(pred, NeRF_Predictor) else None
+        state = _pmean_and_apply(state, grads, guard=guard, reduce='sum')
+    return loss, state, _gather_rays(images, scene, rt_args[2])
+
+
+def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, coords, Omega, J, g, dtau, Sigma,
+                        t_start_obs, t_geos, t_injection, scale, impl=None, ray_shard=None):
+    """bhnerf/network.py:566-622: value_and_grad(loss_fn_image) -> pmean -> apply_gradients.
+    Returns (loss, state, images).  ray_shard = (rank, world): see _ray_sharded_image_step."""
+    pred = state.predictor
+    if ray_shard is not None:
+        return _ray_sharded_image_step(state, t_units, dtype, target, sigma, offset, t_frames,
+                                       (coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection), scale, impl,
+                                       ray_shard, update=True)
     scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units,
                        device=state.flat.device)
-    if _USE_GRAPHS and isinstance(pred, NeRF_Predictor) and _dist() is None and dtype in ('full', 'lc'):
+    if _USE_GRAPHS and isinstance(pred, NeRF_Predictor) and ray_shard is None and dtype in ('full', 'lc'):
         tfh = t_frames if isinstance(t_frames, torch.Tensor) else np.atleast_1d(utils.time_value(t_frames, t_units))
         Bt = int(tfh.numel() if isinstance(tfh, torch.Tensor) else tfh.size)
         step = _graphed_image_step(state, scene, Bt, dtype, scale, impl)
@@ -546,17 +633,50 @@ def gradient_step_image(state, t_units, dtype, target, sigma, offset, t_frames, 
 
 
 def test_image(state, t_units, dtype, target, sigma, offset, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs,
-               t_geos, t_injection, scale, impl=None):
+               t_geos, t_injection, scale, impl=None, ray_shard=None):
     """bhnerf/network.py:684-739: forward + loss only."""
+    if ray_shard is not None:
+        return _ray_sharded_image_step(state, t_units, dtype, target, sigma, offset, t_frames,
+                                       (coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection), scale, impl,
+                                       ray_shard, update=False)
     loss, [images] = loss_fn_image(state.flat, state.predictor.apply, target, sigma, offset, t_frames, coords, Omega,
                                    J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, scale, t_units, dtype, impl)
     return loss, state, images
 
 
+def _ray_sharded_eht_step(state, t_units, dtype, target, sigma, A, t_frames, rt_args, scale, impl, ray_shard, update):
+    """Ray sharding of the eht step: every rank multiplies ITS pixel columns of the per-frame DFT matrices with its block
+    of the images; the (Bt,V) partial visibilities are all-reduced (SUM) before the chi^2, the gradients after it."""
+    pred = state.predictor
+    rank, world = ray_shard
+    scene = _scene_for(pred, *rt_args, t_units, device=state.flat.device, ray_shard=ray_shard)
+    tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
+                         scene.device).reshape(-1)
+    Bt, Pr = tf.numel(), scene.P
+    A = engine._c64(A, scene.device)
+    A_r = A[..., rank * Pr:(rank + 1) * Pr].contiguous()                 # this rank's pixel columns
+    A_r = _eht_prepare(scene, target, sigma, A_r, dtype, Bt)
+    n = A_r.shape[0]
+    images, e, acts = pred._render_fwd(scene, state.flat, tf, impl, save_acts=update)
+    vis = engine.allreduce_sum(engine.vis_fwd(A_r, images.reshape(n, 1, Pr)))
+    tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
+    loss, dvis = engine.loss_vis(vis, _eht_rows(tgt, n), _eht_rows(_eht_sigma(sigma, tgt, scene.device), n), float(scale), dtype)
+    if update:
+        dI = engine.vis_bwd(A_r, dvis, Pr).reshape(images.shape)
+        grads = pred._render_bwd(scene, state.flat, tf, dI, e, acts, impl)
+        guard = engine.step_guard(scene.device, impl) if isinstance(pred, NeRF_Predictor) else None
+        state = _pmean_and_apply(state, grads, guard=guard, reduce='sum')
+    return loss, state, _gather_rays(images, scene, rt_args[2])
+
+
 def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords, Omega, J, g, dtau, Sigma,
-                      t_start_obs, t_geos, t_injection, scale, impl=None):
+                      t_start_obs, t_geos, t_injection, scale, impl=None, ray_shard=None):
     """bhnerf/network.py:624-682."""
     pred = state.predictor
+    if ray_shard is not None:
+        return _ray_sharded_eht_step(state, t_units, dtype, target, sigma, A, t_frames,
+                                     (coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection), scale, impl,
+                                     ray_shard, update=True)
     scene = _scene_for(pred, coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection, t_units,
                        device=state.flat.device)
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
@@ -589,8 +709,12 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
 
 
 def test_eht(state, t_units, dtype, target, sigma, A, t_frames, coords, Omega, J, g, dtau, Sigma, t_start_obs,
-             t_geos, t_injection, scale, impl=None):
+             t_geos, t_injection, scale, impl=None, ray_shard=None):
     """bhnerf/network.py:741-795."""
+    if ray_shard is not None:
+        return _ray_sharded_eht_step(state, t_units, dtype, target, sigma, A, t_frames,
+                                     (coords, Omega, J, g, dtau, Sigma, t_start_obs, t_geos, t_injection), scale, impl,
+                                     ray_shard, update=False)
     loss, [images] = loss_fn_eht(state.flat, state.predictor.apply, target, sigma, A, t_frames, coords, Omega, J, g,
                                  dtau, Sigma, t_start_obs, t_geos, t_injection, scale, t_units, dtype, impl)
     return loss, state, images

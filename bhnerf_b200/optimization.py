@@ -38,15 +38,24 @@ def device_count():
     return _world()[1]
 
 
+def ray_sharded(n_frames):
+    """True when a batch of n_frames cannot be split over the ranks by frames (fewer frames than ranks, or not a
+    multiple): the step then shards RAYS instead (network._ray_sharded_image_step) -- every rank keeps the whole batch.
+    The reference has no such mode: its shard() simply fails (optimization.py:360-362), which is why its own scripts'
+    batchsize 6 cannot use 8 devices."""
+    return _world()[1] > 1 and n_frames % _world()[1] != 0
+
+
 def shard(xs):
     """optimization.py:360-362 reshapes to (ndev, -1, ...) and pmap gives device d the d-th slice; here the
-    calling rank gets its slice directly.  The batch must divide evenly, as in the reference."""
+    calling rank gets its slice directly.  A batch that does not divide evenly is left whole on every rank
+    (ray sharding, see ray_sharded)."""
     rank, world = _world()
 
     def one(x):
         n = x.shape[0]
         if n % world:
-            raise ValueError('batch of %d frames is not divisible by %d devices' % (n, world))
+            return x
         per = n // world
         return x[rank * per:(rank + 1) * per]
     if isinstance(xs, (list, tuple)):
@@ -157,10 +166,11 @@ class TrainStep(object):
             raytracing_args = [raytracing_args[int(_same_on_all_ranks(np.random.choice(len(raytracing_args))))]]
         else:
             call_fn = self.test_pmap
+        kw = {'ray_shard': _world()} if ray_sharded(len(np.atleast_1d(indices))) else {}
         for rt_arg in raytracing_args:
             for i in range(self.num_losses):
                 loss, state, images = call_fn[i](state, self.t_units, self.dtype[i], *self.args[i][indices],
-                                                 *rt_arg.values(), self.scale[i])
+                                                 *rt_arg.values(), self.scale[i], **kw)
                 total_loss = total_loss + loss / len(raytracing_args)
                 total_images = total_images + images / len(raytracing_args)
         return total_loss, state, total_images

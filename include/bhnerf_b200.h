@@ -197,6 +197,28 @@ int bhnerf_adam_step_dev(float* params, const float* grads, float* mu, float* nu
                          int32_t* count_dev, float lr_init, float lr_final, int32_t transition_steps,
                          float b1, float b2, float eps, float grad_scale, const int32_t* guard, void* stream);
 
+/* ---- gradient exchange across ranks (one process per GPU): replaces jax.lax.pmean(grads, 'batch')
+ * (bhnerf/network.py:620, :680).  One NCCL all-reduce on `stream` (CUDA-graph capturable); NCCL is resolved with dlopen
+ * at the first call.  Rank 0 calls bhnerf_comm_unique_id, the host side broadcasts the BHNERF_COMM_ID_BYTES bytes
+ * (any out-of-band channel), every rank calls bhnerf_comm_init with its rank -- collectively, like ncclCommInitRank.
+ * allreduce_mean: buf[n] <- mean over ranks (in place).  allreduce_sum: buf[n] <- sum over ranks: the partial
+ * lightcurves / visibilities of ray sharding (each rank renders P/world rays of every frame).    */
+#define BHNERF_COMM_ID_BYTES 128
+int bhnerf_comm_unique_id(void* id_host);
+int bhnerf_comm_init(int32_t rank, int32_t world, const void* id_host, void** comm_out_host);
+int bhnerf_comm_destroy(void* comm);
+int bhnerf_allreduce_mean(float* buf, int64_t n, void* comm, void* stream);
+int bhnerf_allreduce_sum(float* buf, int64_t n, void* comm, void* stream);
+
+/* ---- lightcurves of rendered images, and the 'lc' loss from them: the two halves of bhnerf_loss_image(kind = LC)
+ * (bhnerf/network.py:478-480), split so that ray-sharded ranks can all-reduce their partial lightcurves in between.
+ * lightcurve: lc[Bt,S] = sum_p images[Bt,S,P] (overwritten).  loss_lightcurve: loss[1] = scale*sum|(lc-t-off)/sigma|^2
+ * and d_images[Bt,S,P] = 2*scale*(lc-t-off)/sigma^2 for every ray (both overwritten).                             */
+int bhnerf_lightcurve(const float* images, int32_t Bt, int32_t S, int32_t P, float* lc, void* stream);
+int bhnerf_loss_lightcurve(const float* lc, const float* target, const float* sigma, const float* offset,
+                           float loss_scale, int32_t Bt, int32_t S, int32_t P, float* loss, float* d_images,
+                           void* stream);
+
 /* ---- accounting for benchmarks: kernels launched by this library, and (between begin/end) CUDA-event
  * time per category {0 render fwd, 1 render bwd, 2 wgrad (SIMT only), 3 heads, 4 misc}.
  * profile_end synchronises the device.  ms_host/scopes_host/launches_host: host arrays of 5.   */

@@ -46,4 +46,41 @@ for case, kind in (('case_image_full', 'full'), ('case_lc_QU', 'lc')):
     ok = torch.tensor([int(upd_err < 2e-2 and torch.equal(ref, state.flat))], device='cuda')
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     assert ok.item() == 1
+
+# ---- ray sharding: 3 frames on `world` ranks cannot be split by frames -> every rank renders all 3
+# frames for its block of rays; partial lightcurves / visibilities are all-reduced before the loss, gradients (SUM) after.
+# The result must equal ONE device's step on the 3 frames: oracle value_and_grad + Adam, live on the CPU (checker only).
+idx = np.arange(3)
+for case, kind in (('case_image_full', 'full'), ('case_lc_QU', 'lc'), ('case_vis', 'vis')):
+    d = np.load(os.path.join(G, case + '.npz'))
+    J = d['J'] if 'J' in d.files else 1.0
+    prd = dict(scale=float(d['scale']), rmin=float(d['rmin']), rmax=float(d['rmax']), z_width=float(d['z_width']))
+    pred = network.NeRF_Predictor(prd['scale'], prd['rmin'], prd['rmax'], prd['z_width'])
+    state = pred.init_state(network.unflatten_params(d['params_flat']), num_iters=100, lr_init=1e-3, lr_final=1e-5)
+    rt = OrderedDict(coords=geo['coords'], Omega=geo['Omega'], J=J, g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
+                     t_start_obs=float(d['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d['t_injection']))
+    params = O.unflatten_params(d['params_flat'])
+    if kind == 'vis':
+        ts = optimization.TrainStep.eht_arrays(d['t_frames'], d['target'], d['sigma'], d['A'], dtype='vis')
+        ref = O.value_and_grad(params, 'eht', 'vis', d['target'][idx], d['sigma'][idx], d['A'][idx], d['t_frames'][idx], dict(rt), prd)
+    else:
+        sig = d['sigma'] if 'sigma' in d.files else np.ones_like(d['target'])
+        ts = optimization.TrainStep.image(d['t_frames'], d['target'], sigma=sig, dtype=kind)
+        ref = O.value_and_grad(params, 'image', kind, d['target'][idx], sig[idx], np.zeros_like(d['target'][idx]),
+                               d['t_frames'][idx], dict(rt), prd)
+    assert optimization.ray_sharded(len(idx))
+    loss, state, images = ts(state, rt, idx)
+    want, _, _ = O.adam_step(d['params_flat'].astype(np.float64), ref['grads'], np.zeros(55169), np.zeros(55169), 0, 1e-3, 1e-5, 100)
+    got = state.flat.cpu().numpy().astype(np.float64)
+    upd_err = np.abs((got - d['params_flat']) - (want - d['params_flat'])).max() / 1e-3
+    img_err = np.abs(images.cpu().numpy().reshape(ref['images'].shape) - ref['images']).max() / np.abs(ref['images']).max()
+    loss_err = abs(loss.item() - ref['loss']) / abs(ref['loss'])
+    chk = state.flat.clone(); dist.broadcast(chk, src=0)
+    good = bool(upd_err < 2e-2 and img_err < 1e-4 and loss_err < 2e-4 and torch.equal(chk, state.flat))
+    if rank == 0:
+        print('ray-sharded %s  world=%d  frames=3 on every rank  loss rel err %.2e  image err %.2e  Adam update err %.2e of lr  %s'
+              % (case, world, loss_err, img_err, upd_err, 'ok' if good else 'FAILED'), flush=True)
+    ok = torch.tensor([int(good)], device='cuda')
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    assert ok.item() == 1
 dist.destroy_process_group()

@@ -106,11 +106,27 @@ class S:                                          # minimal state stub (no GPU o
     def apply_gradients(self, grads, grad_scale=1.0): self.g = grads * grad_scale; return self
 s = network._pmean_and_apply(S(), g)
 assert torch.allclose(s.g, torch.full((5,), 1.5)), s.g
+# a batch the ranks cannot split by frames stays whole on every rank: the step then shards RAYS (SURVEY s8e(2));
+# the reference's shard() cannot run it at all (optimization.py:360-362)
+assert opt.ray_sharded(3) and not opt.ray_sharded(4) and opt.ray_sharded(1)
+assert opt.shard(np.zeros((3, 2))).shape == (3, 2)
+whole, tfw = a[idx[:3]]
+assert whole.shape == (3, 3) and tfw.shape == (3,)
+# this rank's contiguous block of rays of (A,B,G) / (3,A,B,G) / (S,A,B,G) arrays, ray-major
+om = np.arange(4 * 6 * 5, dtype=np.float32).reshape(4, 6, 5)
+blk = network._ray_block(om, (rank, 2), 0)
+assert blk.shape == (12, 1, 5)
+np.testing.assert_array_equal(blk.reshape(12, 5), om.reshape(24, 5)[rank * 12:(rank + 1) * 12])
+co = np.stack([om, om + 1000, om + 2000])
+np.testing.assert_array_equal(network._ray_block(co, (rank, 2), 1).reshape(3, 12, 5), co.reshape(3, 24, 5)[:, rank * 12:(rank + 1) * 12])
 try:
-    opt.shard(np.zeros((3, 2)))
-    raise SystemExit('shard should reject 3 frames on 2 ranks')
+    network._ray_block(np.zeros((3, 3, 2)), (rank, 2), 0)
+    raise SystemExit('9 rays on 2 ranks should be rejected')
 except ValueError:
     pass
+# the ray-sharded gradient exchange is a SUM (per-rank gradients are partial sums of one device's gradient)
+s2 = network._pmean_and_apply(S(), torch.full((5,), float(rank + 1)), reduce='sum')
+assert torch.allclose(s2.g, torch.full((5,), 3.0)), s2.g
 assert opt.device_count() == 2
 loss = opt._allreduce_scalar(torch.tensor([float(rank + 1)]))
 assert loss == 3.0

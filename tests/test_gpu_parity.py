@@ -670,8 +670,9 @@ def test_multi_loss_train_step_image_plus_visibilities():
 
 
 def test_two_rank_nccl_step_matches_oracle():
-    """Frame-sharded step on 2 GPUs (NCCL all-reduce mean + Adam) against the oracle; needs a 2-GPU box (skipped otherwise;
-    last run recorded in profiles/r1_multirank_check_v6.log)."""
+    """Frame-sharded step on 2 GPUs (bhnerf_allreduce_mean below the C ABI, inside the captured CUDA graph, + Adam) and the
+    ray-sharded steps ('full', 'lc', 'vis': 3 frames on 2 ranks) against the oracle; needs a 2-GPU box (skipped otherwise;
+    last run recorded in profiles/r2_multirank_check.log)."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import subprocess
@@ -682,3 +683,4 @@ def test_two_rank_nccl_step_matches_oracle():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count('ranks identical: True') == 2
+    assert r.stdout.count('ray-sharded') == 3 and 'FAILED' not in r.stdout

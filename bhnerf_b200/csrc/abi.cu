@@ -26,7 +26,7 @@ extern "C" int bhnerf_device_check(int* sm_count, int* cc_major, int* cc_minor) 
 #include <mutex>
 #include <vector>
 static std::mutex g_prof_mu;
-static unsigned long long g_launches[BH_NCAT] = {0, 0, 0, 0, 0};
+static unsigned long long g_launches[BH_NCAT] = {0};
 static bool g_prof_on = false;
 struct ProfRec { int cat; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof_recs;
@@ -57,7 +57,7 @@ extern "C" int bhnerf_profile_begin(void) {
   g_prof_on = true;
   return 0;
 }
-// ms[5], scopes[5] (timed launch groups), launches[5] (kernels launched) per category since profile_begin
+// ms, scopes (timed launch groups), launches (kernels launched): BHNERF_N_CATEGORIES entries each, since profile_begin
 extern "C" int bhnerf_profile_end(double* ms_host, int64_t* scopes_host, int64_t* launches_host) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   BH_CHECK_CUDA(cudaDeviceSynchronize());

@@ -77,7 +77,7 @@ extern "C" int bhnerf_comm_destroy(void* comm) {
 extern "C" int bhnerf_allreduce_mean(float* buf, int64_t n, void* comm, void* stream) {
   BH_REQUIRE(buf && comm && n > 0, "allreduce_mean: bad argument");
   if (int r = load_nccl()) return r;
-  BhProfScope ps(BH_CAT_MISC, 1, (cudaStream_t)stream);
+  BhProfScope ps(BH_CAT_COMM, 1, (cudaStream_t)stream);
   BH_CHECK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclAvg, (ncclComm_t)comm, (cudaStream_t)stream));
   return 0;
 }
@@ -85,7 +85,7 @@ extern "C" int bhnerf_allreduce_mean(float* buf, int64_t n, void* comm, void* st
 extern "C" int bhnerf_allreduce_sum(float* buf, int64_t n, void* comm, void* stream) {
   BH_REQUIRE(buf && comm && n > 0, "allreduce_sum: bad argument");
   if (int r = load_nccl()) return r;
-  BhProfScope ps(BH_CAT_MISC, 1, (cudaStream_t)stream);
+  BhProfScope ps(BH_CAT_COMM, 1, (cudaStream_t)stream);
   BH_CHECK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, (ncclComm_t)comm, (cudaStream_t)stream));
   return 0;
 }

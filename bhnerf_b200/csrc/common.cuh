@@ -39,7 +39,9 @@ void bh_set_error(const char* fmt, ...);
   } while (0)
 
 // ---- launch accounting + optional per-category CUDA-event timing (bench.py's live roofline) ----
-enum { BH_CAT_FWD = 0, BH_CAT_BWD = 1, BH_CAT_WGRAD = 2, BH_CAT_HEADS = 3, BH_CAT_MISC = 4, BH_NCAT = 5 };
+enum { BH_CAT_FWD = 0, BH_CAT_BWD = 1, BH_CAT_WGRAD = 2, BH_CAT_HEADS = 3, BH_CAT_MISC = 4, BH_CAT_COMM = 5, BH_CAT_VIS = 6,
+       BH_NCAT = BHNERF_N_CATEGORIES };
+static_assert(BH_CAT_VIS + 1 == BH_NCAT, "profile categories");
 void bh_prof_begin(int cat, int n_launches, cudaStream_t st);
 void bh_prof_end(int cat, cudaStream_t st);
 struct BhProfScope {

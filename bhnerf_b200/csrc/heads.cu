@@ -145,54 +145,75 @@ extern "C" int bhnerf_loss_image(const float* images, const float* target, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// visibility head (network.py:542-564): vis[b,v] = sum_p A[b,v,p] * I[b,p], complex64 A.
-// HBM-bound stream of A (8*V*P bytes per frame per pass): one warp per (b,v) row, float4 loads.
+// visibility head (network.py:542-564): vis[b,v] = sum_p A[b,v,p] * I[b,p], complex64 A -- a DIFFERENT DFT matrix per
+// frame (uv coverage rotates with the Earth), so this is a batched GEMV with no operand reuse: the bound is the HBM
+// stream of A, 8*V*P bytes per frame per pass.  Forward: one block per (b,v) row, 16-byte loads, 4 independent loads in
+// flight per thread, deterministic block reduction.  Backward: d_images[b,p] = sum_v Re(conj(A[b,v,p]) d_vis[b,v]); the
+// rows are split into chunks so that a frame gives 8x more blocks than P/512 (fp32 atomics into the zeroed d_images).
+// bhnerf_vis_head runs forward -> chi^2 -> backward per GROUP of frames small enough for the group's A to stay in the
+// 126 MB L2, so the backward's pass over A does not go to HBM again.
 // ---------------------------------------------------------------------------------------------
-__global__ void vis_fwd_kernel(const float2* __restrict__ A, const float* __restrict__ I, int V, int P,
-                               float2* __restrict__ vis) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  int b = blockIdx.y;
-  if (warp >= V) return;
-  const float2* row = A + ((size_t)b * V + warp) * P;
+__global__ void __launch_bounds__(256) vis_fwd_kernel(const float2* __restrict__ A, const float* __restrict__ I, int V, int P,
+                                                      float2* __restrict__ vis) {
+  __shared__ float sh[32];
+  const int v = blockIdx.x, b = blockIdx.y;
+  const float2* row = A + ((size_t)b * V + v) * P;
   const float* img = I + (size_t)b * P;
   float re = 0.f, im = 0.f;
   if ((P & 1) == 0) {
     const float4* row4 = (const float4*)row;
     const float2* img2 = (const float2*)img;
-    for (int q = lane; q < P / 2; q += 32) {
-      float4 a = __ldcs(row4 + q);          // streamed once: evict-first
+    const int n = P / 2;
+    int q = threadIdx.x;
+    for (; q + 3 * 256 < n; q += 4 * 256) {
+      float4 a0 = __ldcs(row4 + q), a1 = __ldcs(row4 + q + 256), a2 = __ldcs(row4 + q + 512), a3 = __ldcs(row4 + q + 768);
+      float2 x0 = img2[q], x1 = img2[q + 256], x2 = img2[q + 512], x3 = img2[q + 768];
+      re += a0.x * x0.x + a0.z * x0.y + a1.x * x1.x + a1.z * x1.y + a2.x * x2.x + a2.z * x2.y + a3.x * x3.x + a3.z * x3.y;
+      im += a0.y * x0.x + a0.w * x0.y + a1.y * x1.x + a1.w * x1.y + a2.y * x2.x + a2.w * x2.y + a3.y * x3.x + a3.w * x3.y;
+    }
+    for (; q < n; q += 256) {
+      float4 a = __ldcs(row4 + q);
       float2 x = img2[q];
       re += a.x * x.x + a.z * x.y;
       im += a.y * x.x + a.w * x.y;
     }
   } else {
-    for (int p = lane; p < P; p += 32) { float2 a = row[p]; float x = img[p]; re += a.x * x; im += a.y * x; }
+    for (int p = threadIdx.x; p < P; p += 256) { float2 a = row[p]; float x = img[p]; re += a.x * x; im += a.y * x; }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    re += __shfl_xor_sync(0xffffffffu, re, o);
-    im += __shfl_xor_sync(0xffffffffu, im, o);
-  }
-  if (lane == 0) vis[(size_t)b * V + warp] = make_float2(re, im);
+  re = block_reduce_sum(re, sh);
+  im = block_reduce_sum(im, sh);
+  if (threadIdx.x == 0) vis[(size_t)b * V + v] = make_float2(re, im);
 }
 
-// d_images[b,p] = sum_v Re(conj(A[b,v,p]) * d_vis[b,v]) = sum_v A.re*dv.re + A.im*dv.im
-__global__ void vis_bwd_kernel(const float2* __restrict__ A, const float2* __restrict__ dvis, int V, int P,
-                               float* __restrict__ dI) {
-  extern __shared__ float2 dv_s[];
-  int b = blockIdx.y;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) dv_s[v] = dvis[(size_t)b * V + v];
+#define VIS_BWD_ROWS 24       // rows of A per block of the backward
+__global__ void __launch_bounds__(256) vis_bwd_kernel(const float2* __restrict__ A, const float2* __restrict__ dvis, int V, int P,
+                                                      float* __restrict__ dI) {
+  __shared__ float2 dv_s[VIS_BWD_ROWS];
+  const int b = blockIdx.z, v0 = blockIdx.y * VIS_BWD_ROWS, nv = min(VIS_BWD_ROWS, V - v0);
+  if (threadIdx.x < nv) dv_s[threadIdx.x] = dvis[(size_t)b * V + v0 + threadIdx.x];
   __syncthreads();
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = (blockIdx.x * 256 + threadIdx.x) * 2;          // two pixels per thread: 16-byte loads
   if (p >= P) return;
-  const float2* col = A + (size_t)b * V * P + p;
-  float acc = 0.f;
+  const float2* col = A + ((size_t)b * V + v0) * P + p;
+  float acc0 = 0.f, acc1 = 0.f;
+  if (p + 1 < P && (P & 1) == 0) {
 #pragma unroll 4
-  for (int v = 0; v < V; ++v) {
-    float2 a = __ldcs(col + (size_t)v * P);
-    acc += a.x * dv_s[v].x + a.y * dv_s[v].y;
+    for (int v = 0; v < nv; ++v) {
+      const float4 a = __ldg((const float4*)(col + (size_t)v * P));       // second pass over A: expected in L2
+      acc0 += a.x * dv_s[v].x + a.y * dv_s[v].y;
+      acc1 += a.z * dv_s[v].x + a.w * dv_s[v].y;
+    }
+    atomicAdd(dI + (size_t)b * P + p, acc0);
+    atomicAdd(dI + (size_t)b * P + p + 1, acc1);
+  } else {
+    for (int v = 0; v < nv; ++v) {
+      const float2 a = col[(size_t)v * P];
+      acc0 += a.x * dv_s[v].x + a.y * dv_s[v].y;
+      if (p + 1 < P) { const float2 a1 = col[(size_t)v * P + 1]; acc1 += a1.x * dv_s[v].x + a1.y * dv_s[v].y; }
+    }
+    atomicAdd(dI + (size_t)b * P + p, acc0);
+    if (p + 1 < P) atomicAdd(dI + (size_t)b * P + p + 1, acc1);
   }
-  dI[(size_t)b * P + p] = acc;
 }
 
 // 'vis': chisq = sum (|vis - t|/sigma)^2 ; 'amp': chisq = sum |(|vis| - t)/sigma|^2
@@ -265,42 +286,82 @@ extern "C" int bhnerf_add_inplace(float* dst, const float* src, int32_t n, void*
   return 0;
 }
 
-extern "C" int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, int32_t V, int32_t P, float* vis,
-                              void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  BhProfScope ps(BH_CAT_HEADS, 1, st);
-  dim3 grid((V * 32 + 255) / 256, Bt);
-  vis_fwd_kernel<<<grid, 256, 0, st>>>((const float2*)A, images, V, P, (float2*)vis);
+static int launch_vis_fwd(const float* A, const float* images, int Bt, int V, int P, float* vis, cudaStream_t st) {
+  BhProfScope ps(BH_CAT_VIS, 1, st);
+  vis_fwd_kernel<<<dim3(V, Bt), 256, 0, st>>>((const float2*)A, images, V, P, (float2*)vis);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+extern "C" int bhnerf_vis_fwd(const float* A, const float* images, int32_t Bt, int32_t V, int32_t P, float* vis,
+                              void* stream) {
+  BH_REQUIRE(A && images && vis && Bt > 0 && V > 0 && P > 0 && Bt <= 65535, "vis_fwd: bad argument");
+  return launch_vis_fwd(A, images, Bt, V, P, vis, (cudaStream_t)stream);
+}
 
+static int launch_loss_vis(const float* vis, const float* target, const float* sigma, float loss_scale, int kind, int Bt,
+                           int V, float* loss, float* d_vis, cudaStream_t st);
 extern "C" int bhnerf_loss_vis(const float* vis, const float* target, const float* sigma, float loss_scale,
                                int32_t kind, int32_t Bt, int32_t V, float* loss, float* d_vis, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BH_REQUIRE(kind == BHNERF_LOSS_VIS || kind == BHNERF_LOSS_AMP || kind == BHNERF_LOSS_CPHASE,
              "loss_vis: eht dtype (%d) not supported", kind);
   BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  return launch_loss_vis(vis, target, sigma, loss_scale, kind, Bt, V, loss, d_vis, st);
+}
+
+static int launch_vis_bwd(const float* A, const float* d_vis, int Bt, int V, int P, float* d_images, cudaStream_t st) {
+  BH_CHECK_CUDA(cudaMemsetAsync(d_images, 0, (size_t)Bt * P * sizeof(float), st));
+  BhProfScope ps(BH_CAT_VIS, 1, st);
+  dim3 grid((P / 2 + 255) / 256 + ((P & 1) ? 1 : 0), (V + VIS_BWD_ROWS - 1) / VIS_BWD_ROWS, Bt);
+  vis_bwd_kernel<<<grid, 256, 0, st>>>((const float2*)A, (const float2*)d_vis, V, P, d_images);
+  BH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, int32_t V, int32_t P,
+                              float* d_images, void* stream) {
+  BH_REQUIRE(A && d_vis && d_images && Bt > 0 && V > 0 && P > 0 && Bt <= 65535, "vis_bwd: bad argument");
+  return launch_vis_bwd(A, d_vis, Bt, V, P, d_images, (cudaStream_t)stream);
+}
+
+static int launch_loss_vis(const float* vis, const float* target, const float* sigma, float loss_scale, int kind, int Bt,
+                           int V, float* loss, float* d_vis, cudaStream_t st) {
   int n = Bt * V;
   int blocks = (n + 255) / 256; if (blocks > 592) blocks = 592;
-  BhProfScope ps(BH_CAT_HEADS, 1, st);
+  BhProfScope ps(BH_CAT_VIS, 1, st);
   if (kind == BHNERF_LOSS_CPHASE)
     loss_cphase_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, V, n, loss, (float2*)d_vis);
   else
-    loss_vis_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, kind, n, loss,
-                                            (float2*)d_vis);
+    loss_vis_kernel<<<blocks, 256, 0, st>>>((const float2*)vis, target, sigma, loss_scale, kind, n, loss, (float2*)d_vis);
   BH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, int32_t V, int32_t P,
-                              float* d_images, void* stream) {
+// The whole eht head of a step in one call: per group of frames  vis = A I  ->  chi^2 (accumulated)  ->  d_images = A^H d_vis.
+// rows = rows of A per frame (V for 'vis'/'amp', 3*ncphase for 'cphase'); target stride per frame is rows ('vis': complex)
+// or rows/3 ('cphase').  group_bytes: how much of A one group may cover (0 = 48 MB: less than half of the 126 MB L2).
+extern "C" int bhnerf_vis_head(const float* A, const float* images, const float* target, const float* sigma,
+                               float loss_scale, int32_t kind, int32_t Bt, int32_t rows, int32_t P, float* loss,
+                               float* vis, float* d_vis, float* d_images, size_t group_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  BH_REQUIRE((size_t)V * sizeof(float2) <= 48 * 1024, "vis_bwd: V=%d too large", V);
-  BhProfScope ps(BH_CAT_HEADS, 1, st);
-  dim3 grid((P + 255) / 256, Bt);
-  vis_bwd_kernel<<<grid, 256, V * sizeof(float2), st>>>((const float2*)A, (const float2*)d_vis, V, P, d_images);
-  BH_CHECK_CUDA(cudaGetLastError());
+  BH_REQUIRE(A && images && target && sigma && loss && vis && d_vis && Bt > 0 && rows > 0 && P > 0, "vis_head: bad argument");
+  BH_REQUIRE(kind == BHNERF_LOSS_VIS || kind == BHNERF_LOSS_AMP || kind == BHNERF_LOSS_CPHASE,
+             "vis_head: eht dtype (%d) not supported", kind);
+  BH_REQUIRE(kind != BHNERF_LOSS_CPHASE || rows % 3 == 0, "vis_head: cphase needs rows = 3 * ncphase");
+  if (group_bytes == 0) group_bytes = (size_t)48 << 20;
+  const size_t frame_bytes = (size_t)rows * P * 8;
+  int Bg = (int)(group_bytes / frame_bytes); if (Bg < 1) Bg = 1; if (Bg > Bt) Bg = Bt;
+  const int V = kind == BHNERF_LOSS_CPHASE ? rows / 3 : rows;              // targets per frame
+  const size_t tstride = (size_t)V * (kind == BHNERF_LOSS_VIS ? 2 : 1);
+  BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  for (int b0 = 0; b0 < Bt; b0 += Bg) {
+    const int nb = Bt - b0 < Bg ? Bt - b0 : Bg;
+    const float* Ag = A + (size_t)b0 * rows * P * 2;
+    float* visg = vis + (size_t)b0 * rows * 2;
+    float* dvisg = d_vis + (size_t)b0 * rows * 2;
+    if (int r = launch_vis_fwd(Ag, images + (size_t)b0 * P, nb, rows, P, visg, st)) return r;
+    if (int r = launch_loss_vis(visg, target + (size_t)b0 * tstride, sigma + (size_t)b0 * V, loss_scale, kind, nb, V, loss, dvisg, st)) return r;
+    if (d_images) { if (int r = launch_vis_bwd(Ag, dvisg, nb, rows, P, d_images + (size_t)b0 * P, st)) return r; }
+  }
   return 0;
 }
 

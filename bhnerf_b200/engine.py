@@ -289,6 +289,29 @@ def loss_vis(vis, target, sigma, scale, kind):
     return loss, dvis
 
 
+def vis_head(A, images, target, sigma, scale, kind, want_grad=True, group_bytes=0):
+    """The eht head of a step in one C-ABI call (bhnerf_vis_head): per L2-sized group of frames vis = A I -> chi^2 ->
+    d_images = A^H d_vis.  A [n, rows, P] complex64 (n = frames x polarizations), images [n, 1, P] / [n, P]; target / sigma
+    [n, V] (V = rows, or rows/3 for 'cphase').  Returns (loss[1], vis [n, rows], d_images [n, 1, P] or None)."""
+    lib = _lib.load(); dev = images.device
+    n, rows, P = A.shape
+    k = LOSS_KINDS[kind] if isinstance(kind, str) else kind
+    V = rows // 3 if k == LOSS_KINDS['cphase'] else rows
+    target = _c64(target, dev) if k == LOSS_KINDS['vis'] else _dev_f32(target, dev)
+    sigma = _dev_f32(sigma, dev)
+    if sigma.numel() == 1:
+        sigma = sigma.reshape(1).expand(n * V).contiguous()
+    assert target.numel() == n * V and sigma.numel() == n * V and images.numel() == n * P
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    vis = torch.empty((n, rows), dtype=torch.complex64, device=dev)
+    dvis = torch.empty_like(vis)
+    dI = torch.empty((n, 1, P), dtype=torch.float32, device=dev) if want_grad else None
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_vis_head(_ptr(A), _ptr(images), _ptr(target), _ptr(sigma), float(scale), k, n, rows, P, _ptr(loss),
+                                  _ptr(vis), _ptr(dvis), _ptr(dI), int(group_bytes), _stream()))
+    return loss, vis, dI
+
+
 def vis_bwd(A, dvis, P):
     lib = _lib.load(); dev = dvis.device
     Bt, V = dvis.shape

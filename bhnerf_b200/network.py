@@ -412,9 +412,9 @@ def loss_fn_eht(params, predictor_fn, target, sigma, A, t_frames, coords, Omega,
     A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
     images, _, _ = pred._render_fwd(scene, _flat(params, scene.device, pred), tf, impl)
     n = A.shape[0]                                           # frames x polarizations
-    vis = engine.vis_fwd(A, images.reshape(n, 1, scene.P))
     tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
-    loss, _ = engine.loss_vis(vis, _eht_rows(tgt, n), _eht_rows(_eht_sigma(sigma, tgt, scene.device), n), float(scale), dtype)
+    loss, _, _ = engine.vis_head(A, images.reshape(n, 1, scene.P), _eht_rows(tgt, n),
+                                 _eht_rows(_eht_sigma(sigma, tgt, scene.device), n), float(scale), dtype, want_grad=False)
     return loss, [_shape_images(images, scene, J)]
 
 
@@ -695,9 +695,8 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
         rows = slice(b0 * npol, min(b0 + Bc, Bt) * npol)
         images, e, acts = pred._render_fwd(scene, state.flat, tf[sl], impl, save_acts=not isinstance(pred, GRID_Predictor))
         A_c = A[rows].contiguous()
-        vis = engine.vis_fwd(A_c, images.reshape(A_c.shape[0], 1, scene.P))
-        l, dvis = engine.loss_vis(vis, tgt[rows], sig[rows], float(scale), dtype)
-        dI = engine.vis_bwd(A_c, dvis, scene.P).reshape(images.shape)
+        l, _, dI = engine.vis_head(A_c, images.reshape(A_c.shape[0], 1, scene.P), tgt[rows], sig[rows], float(scale), dtype)
+        dI = dI.reshape(images.shape)
         g = pred._render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)
         loss = l if loss is None else engine.add_inplace(loss, l)       # per-chunk partials accumulate on the device
         grads = g if grads is None else engine.add_inplace(grads, g)

@@ -77,12 +77,14 @@ def flat_geodesics(spin, inc_deg, fov, n, G, r_o=1000.0, n_beta=None):
                 t_geos=f32(t_geos), r=f32(r))
 
 
-def make_config(name, seed=0, frame_offset=0.0, nt=None):
+def make_config(name, seed=0, frame_offset=0.0, nt=None, inc=None):
     """Inputs for one BASELINE.json config: raytracing args (reference positional order), predictor
-    constants, frame times and seeded targets."""
+    constants, frame times and seeded targets.  `inc` overrides the inclination [deg] (ensemble sweeps)."""
     c = dict(CONFIGS[name])
     if nt is not None:
         c['nt'] = nt
+    if inc is not None:
+        c['inc'] = float(inc)
     geo = flat_geodesics(c['spin'], c['inc'], c['fov'], c['n'], c['G'])
     A = B = c['n']
     rng = np.random.default_rng(seed)

@@ -116,6 +116,15 @@ int bhnerf_loss_vis(const float* vis, const float* target, const float* sigma, f
 int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, int32_t V, int32_t P,
                    float* d_images, void* stream);
 
+/* The whole eht head of a step in one call (loss_fn_eht after image_plane_prediction, network.py:542-564, and its
+ * pull-back to the images): per GROUP of frames  vis = A I -> chi^2 (accumulated into loss[1]) -> d_images = A^H d_vis,
+ * the group sized (group_bytes of A, 0 = 48 MB) so that the backward's second pass over A is served by the L2 instead of
+ * HBM.  rows = rows of A per frame: nvis ('vis','amp') or 3*ncphase ('cphase'); a polarization axis folds into Bt.
+ * vis / d_vis [Bt,rows] complex64 scratch+output; d_images [Bt,P] overwritten (NULL: forward + loss only).          */
+int bhnerf_vis_head(const float* A, const float* images, const float* target, const float* sigma,
+                    float loss_scale, int32_t kind, int32_t Bt, int32_t rows, int32_t P, float* loss,
+                    float* vis, float* d_vis, float* d_images, size_t group_bytes, void* stream);
+
 /* ---- fused train step for the separable image losses: per frame chunk
  * fwd -> ray integral -> loss -> bwd with activations kept in `workspace`.  Replaces
  * gradient_step_image up to (not including) pmean/apply_gradients (network.py:617-619).
@@ -220,8 +229,10 @@ int bhnerf_loss_lightcurve(const float* lc, const float* target, const float* si
                            void* stream);
 
 /* ---- accounting for benchmarks: kernels launched by this library, and (between begin/end) CUDA-event
- * time per category {0 render fwd, 1 render bwd, 2 wgrad (SIMT only), 3 heads, 4 misc}.
- * profile_end synchronises the device.  ms_host/scopes_host/launches_host: host arrays of 5.   */
+ * time per category {0 render fwd, 1 render bwd, 2 wgrad (two-kernel backward), 3 heads (ray integral, image losses,
+ * d loss/d o), 4 misc, 5 collectives (bhnerf_allreduce_*), 6 visibility head}.
+ * profile_end synchronises the device.  ms_host/scopes_host/launches_host: host arrays of BHNERF_N_CATEGORIES.   */
+#define BHNERF_N_CATEGORIES 7
 int64_t bhnerf_launch_count(void);
 int bhnerf_profile_begin(void);
 int bhnerf_profile_end(double* ms_host, int64_t* scopes_host, int64_t* launches_host);

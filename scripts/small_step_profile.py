@@ -34,7 +34,7 @@ for it in range(N):
     engine.train_step_image(scene, params, tf, tgt, sig, off, 1.0, 'full', out=out)
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
-ms = (ctypes.c_double * 5)(); sc = (ctypes.c_int64 * 5)(); ln = (ctypes.c_int64 * 5)()
+ms = (ctypes.c_double * 7)(); sc = (ctypes.c_int64 * 7)(); ln = (ctypes.c_int64 * 7)()
 lib.bhnerf_profile_end(ms, sc, ln)
 names = ['render_fwd', 'render_bwd', 'wgrad', 'heads', 'misc']
 print('planes env=%s  n_active=%d  sample-frames=%d  wall %.3f ms/step' % (os.environ.get('BHNERF_TC_PLANES'), scene.n_active,

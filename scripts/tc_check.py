@@ -94,7 +94,7 @@ def train_big(name='cfg1_tutorial3', nt=8, reps=3):
             out = engine.train_step_image(scene, params, tf, tgt, sig, offd, 1.0, kind, impl)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
-        ms = (ctypes.c_double * 5)(); sc = (ctypes.c_int64 * 5)(); ln = (ctypes.c_int64 * 5)()
+        ms = (ctypes.c_double * 7)(); sc = (ctypes.c_int64 * 7)(); ln = (ctypes.c_int64 * 7)()
         lib.bhnerf_profile_end(ms, sc, ln)
         n = nt * scene.n_active
         print('%s %s train: %.3f ms, %.3e eval samples/s, %.1f TFLOP/s algorithmic; per-step ms fwd %.3f bwd %.3f wgrad %.3f '

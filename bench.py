@@ -387,9 +387,7 @@ def main():
             gbs = head_bytes / head_s / 1e9
             kernels['vis_head'] = {'bound': 'hbm', 'ms_per_step': head_s * 1e3, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                                    'frac': gbs / hbm_peak, 'algorithmic_bytes_per_step': head_bytes,
-                                   'hbm_bytes_per_step_expected': head_bytes / 2,
-                                   'note': 'achieved = algorithmic bytes (two passes over A) / head time; the backward pass '
-                                           're-reads A from L2, so the HBM traffic is about half of it',
+                                   'note': 'achieved = algorithmic bytes (two passes over A: A I and A^H d_vis) / head time',
                                    'launches_per_step': int(cat_sc[CATS.index('vis_head')]) // args.steps}
         kernels = {n: k for n, k in kernels.items() if k['ms_per_step'] > 0}
         dom = max((n for n in kernels if kernels[n]['bound'] == 'tensor'), key=lambda n: kernels[n]['ms_per_step'])

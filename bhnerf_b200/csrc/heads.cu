@@ -150,8 +150,8 @@ extern "C" int bhnerf_loss_image(const float* images, const float* target, const
 // stream of A, 8*V*P bytes per frame per pass.  Forward: one block per (b,v) row, 16-byte loads, 4 independent loads in
 // flight per thread, deterministic block reduction.  Backward: d_images[b,p] = sum_v Re(conj(A[b,v,p]) d_vis[b,v]); the
 // rows are split into chunks so that a frame gives 8x more blocks than P/512 (fp32 atomics into the zeroed d_images).
-// bhnerf_vis_head runs forward -> chi^2 -> backward per GROUP of frames small enough for the group's A to stay in the
-// 126 MB L2, so the backward's pass over A does not go to HBM again.
+// bhnerf_vis_head runs forward -> chi^2 -> backward per GROUP of frames (default: the whole batch; optionally groups small
+// enough for the group's A to stay in the 126 MB L2 for the backward pass).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) vis_fwd_kernel(const float2* __restrict__ A, const float* __restrict__ I, int V, int P,
                                                       float2* __restrict__ vis) {
@@ -338,7 +338,11 @@ static int launch_loss_vis(const float* vis, const float* target, const float* s
 
 // The whole eht head of a step in one call: per group of frames  vis = A I  ->  chi^2 (accumulated)  ->  d_images = A^H d_vis.
 // rows = rows of A per frame (V for 'vis'/'amp', 3*ncphase for 'cphase'); target stride per frame is rows ('vis': complex)
-// or rows/3 ('cphase').  group_bytes: how much of A one group may cover (0 = 48 MB: less than half of the 126 MB L2).
+// or rows/3 ('cphase').  group_bytes: how much of A one group may cover (0 = the whole batch in one group).  Measured on
+// B200 at the cfg3 shape (scripts/vis_head_bench.py, profiles/r2_vis_head_bench.log): both passes stream A at the HBM
+// roofline when the batch is one group (0.49 ms for 2 x 1.6 GB = 6.5 TB/s); groups small enough for the L2 to serve the
+// backward pass (<= 48 MB) lose more to their 3 launches each than the saved HBM pass gains (1.08 ms), so one group is the
+// default and the L2-sized grouping stays an option.
 extern "C" int bhnerf_vis_head(const float* A, const float* images, const float* target, const float* sigma,
                                float loss_scale, int32_t kind, int32_t Bt, int32_t rows, int32_t P, float* loss,
                                float* vis, float* d_vis, float* d_images, size_t group_bytes, void* stream) {
@@ -347,9 +351,8 @@ extern "C" int bhnerf_vis_head(const float* A, const float* images, const float*
   BH_REQUIRE(kind == BHNERF_LOSS_VIS || kind == BHNERF_LOSS_AMP || kind == BHNERF_LOSS_CPHASE,
              "vis_head: eht dtype (%d) not supported", kind);
   BH_REQUIRE(kind != BHNERF_LOSS_CPHASE || rows % 3 == 0, "vis_head: cphase needs rows = 3 * ncphase");
-  if (group_bytes == 0) group_bytes = (size_t)48 << 20;
   const size_t frame_bytes = (size_t)rows * P * 8;
-  int Bg = (int)(group_bytes / frame_bytes); if (Bg < 1) Bg = 1; if (Bg > Bt) Bg = Bt;
+  int Bg = group_bytes == 0 ? Bt : (int)(group_bytes / frame_bytes); if (Bg < 1) Bg = 1; if (Bg > Bt) Bg = Bt;
   const int V = kind == BHNERF_LOSS_CPHASE ? rows / 3 : rows;              // targets per frame
   const size_t tstride = (size_t)V * (kind == BHNERF_LOSS_VIS ? 2 : 1);
   BH_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));

@@ -117,9 +117,10 @@ int bhnerf_vis_bwd(const float* A, const float* d_vis, int32_t Bt, int32_t V, in
                    float* d_images, void* stream);
 
 /* The whole eht head of a step in one call (loss_fn_eht after image_plane_prediction, network.py:542-564, and its
- * pull-back to the images): per GROUP of frames  vis = A I -> chi^2 (accumulated into loss[1]) -> d_images = A^H d_vis,
- * the group sized (group_bytes of A, 0 = 48 MB) so that the backward's second pass over A is served by the L2 instead of
- * HBM.  rows = rows of A per frame: nvis ('vis','amp') or 3*ncphase ('cphase'); a polarization axis folds into Bt.
+ * pull-back to the images): per GROUP of frames  vis = A I -> chi^2 (accumulated into loss[1]) -> d_images = A^H d_vis.
+ * group_bytes = bytes of A per group: 0 = the whole batch (both passes stream A at the HBM roofline, the measured
+ * optimum); a value <= ~48 MB lets the L2 serve the backward pass at the price of 3 launches per group.
+ * rows = rows of A per frame: nvis ('vis','amp') or 3*ncphase ('cphase'); a polarization axis folds into Bt.
  * vis / d_vis [Bt,rows] complex64 scratch+output; d_images [Bt,P] overwritten (NULL: forward + loss only).          */
 int bhnerf_vis_head(const float* A, const float* images, const float* target, const float* sigma,
                     float loss_scale, int32_t kind, int32_t Bt, int32_t rows, int32_t P, float* loss,

@@ -1,9 +1,10 @@
 """The binding a bhnerf maintainer adds so that bhnerf/network.py keeps its JAX API while the hot path runs in
 libbhnerf_b200.so (jax.ffi custom calls over the C ABI of include/bhnerf_b200.h).
 
-NOT importable in this repository's image: jax / jaxlib are not installed, so this file is
-documentation-grade source kept next to integration/xla_ffi_shim.cc; everything it calls is exercised here
-through the ctypes host (bhnerf_b200/_lib.py), which binds the very same C entry points.
+NOT importable in this repository's image: jax / jaxlib are not installed.  What it needs from this
+repository -- bhnerf_b200.jax_scene (prepack, typed scene attributes, workspace sizes) and the C entry points -- exists and
+is exercised here through ctypes; tests/test_abi_host.py checks on the CPU that this file parses, that every name it takes
+from the repository resolves, and that its ffi_call attributes are the ones integration/xla_ffi_shim.cc binds.
 
 Usage inside bhnerf (replaces the body of network.image_plane_prediction, bhnerf/network.py:373-420):
 
@@ -50,14 +51,14 @@ def _render(scene, flat_params, t_frames):
 
 
 def _render_fwd(scene, flat_params, t_frames):
-    """scene: host object from prepack() holding the packed device buffer, the consts attribute and the sizes."""
+    """scene: bhnerf_b200.jax_scene.JaxScene (packed device buffer, typed scalar attributes, workspace sizes)."""
     Bt = t_frames.shape[0]
     out_types = (jax.ShapeDtypeStruct((Bt, scene.S, scene.P), jnp.float32),
                  jax.ShapeDtypeStruct((Bt, scene.n_pad), jnp.float32),
                  jax.ShapeDtypeStruct((scene.acts_bytes(Bt),), jnp.uint8),
                  jax.ShapeDtypeStruct((scene.fwd_workspace_bytes,), jnp.uint8))
-    images, e, acts, _ = jax.ffi.ffi_call('bhnerf_render_fwd', out_types)(scene.packed, flat_params, t_frames,
-                                                                        consts=scene.consts)
+    images, e, acts, _ = jax.ffi.ffi_call('bhnerf_render_fwd', out_types)(scene.as_jax(), flat_params, t_frames,
+                                                                        **scene.attrs)
     return images, (flat_params, t_frames, e, acts)
 
 
@@ -66,8 +67,8 @@ def _render_bwd(scene, res, d_images):
     Bt = t_frames.shape[0]
     out_types = (jax.ShapeDtypeStruct((N_PARAMS,), jnp.float32),
                  jax.ShapeDtypeStruct((scene.bwd_workspace_bytes(Bt),), jnp.uint8))
-    d_params, _ = jax.ffi.ffi_call('bhnerf_render_bwd', out_types)(scene.packed, flat_params, t_frames, d_images, e, acts,
-                                                                  consts=scene.consts)
+    d_params, _ = jax.ffi.ffi_call('bhnerf_render_bwd', out_types)(scene.as_jax(), flat_params, t_frames, d_images, e, acts,
+                                                                  **scene.attrs)
     return d_params, None            # gradient w.r.t. params only (argnums=0, bhnerf/network.py:617)
 
 

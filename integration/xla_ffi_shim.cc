@@ -15,23 +15,35 @@ static ffi::Error to_error(int rc) {
   return rc == 0 ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInternal, bhnerf_last_error());
 }
 
-// The prepacked scene (frame-independent part of network.raytracing_args, bhnerf/network.py:850-894)
-// travels through XLA as an opaque uint8 buffer [sizeof(bhnerf_scene_t) header | packed arrays];
-// bhnerf_prepack is called once per raytracing_args from Python (integration/jax_binding.py).
-static bhnerf_scene_t scene_of(ffi::AnyBuffer packed, ffi::Span<const float> consts) {
-  bhnerf_scene_t sc = *reinterpret_cast<const bhnerf_scene_t*>(consts.begin() + 4);   // host-side header copy
+// The prepacked scene (frame-independent part of network.raytracing_args, bhnerf/network.py:850-894) travels through XLA
+// as an opaque uint8 buffer (the packed arrays) plus TYPED scalar attributes, one per field of bhnerf_scene_t
+// (bhnerf_b200/jax_scene.py: ATTRS); bhnerf_prepack is called once per raytracing_args from Python.
+struct SceneAttrs {
+  int32_t n_active, n_pad, P, G, S;
+  float t_start_obs, GM_c3, t_injection, scale;
+};
+static bhnerf_scene_t scene_of(ffi::AnyBuffer packed, const SceneAttrs& a) {
+  bhnerf_scene_t sc;
   sc.packed = packed.untyped_data();
-  sc.t_start_obs = consts[0]; sc.GM_c3 = consts[1]; sc.t_injection = consts[2]; sc.scale = consts[3];
+  sc.n_active = a.n_active; sc.n_pad = a.n_pad; sc.P = a.P; sc.G = a.G; sc.S = a.S;
+  sc.t_start_obs = a.t_start_obs; sc.GM_c3 = a.GM_c3; sc.t_injection = a.t_injection; sc.scale = a.scale;
   return sc;
 }
+#define BHNERF_SCENE_ATTR_PARAMS                                                                                   \
+  int32_t n_active, int32_t n_pad, int32_t P, int32_t G, int32_t S, float t_start_obs, float GM_c3, float t_injection, \
+      float scale
+#define BHNERF_SCENE_ATTR_VALUES SceneAttrs{n_active, n_pad, P, G, S, t_start_obs, GM_c3, t_injection, scale}
+#define BHNERF_SCENE_ATTR_BINDINGS                                                                                  \
+  .Attr<int32_t>("n_active").Attr<int32_t>("n_pad").Attr<int32_t>("P").Attr<int32_t>("G").Attr<int32_t>("S")         \
+      .Attr<float>("t_start_obs").Attr<float>("GM_c3").Attr<float>("t_injection").Attr<float>("scale")
 
 // images[Bt,S,P], e[Bt,n_pad] = render(packed scene, params[55169], t_frames[Bt])
 // replaces network.image_plane_prediction (bhnerf/network.py:373-420)
 static ffi::Error RenderFwdImpl(cudaStream_t stream, ffi::AnyBuffer packed, ffi::Buffer<ffi::F32> params,
-                                ffi::Buffer<ffi::F32> t_frames, ffi::Span<const float> consts,
+                                ffi::Buffer<ffi::F32> t_frames, BHNERF_SCENE_ATTR_PARAMS,
                                 ffi::ResultBuffer<ffi::F32> images, ffi::ResultBuffer<ffi::F32> e,
                                 ffi::ResultBuffer<ffi::U8> acts, ffi::ResultBuffer<ffi::U8> workspace) {
-  bhnerf_scene_t sc = scene_of(packed, consts);
+  bhnerf_scene_t sc = scene_of(packed, BHNERF_SCENE_ATTR_VALUES);
   const int32_t Bt = static_cast<int32_t>(t_frames.element_count());
   return to_error(bhnerf_render_fwd(&sc, params.typed_data(), t_frames.typed_data(), Bt, images->typed_data(),
                                     e->typed_data(), acts->element_count() ? acts->untyped_data() : nullptr,
@@ -41,9 +53,9 @@ static ffi::Error RenderFwdImpl(cudaStream_t stream, ffi::AnyBuffer packed, ffi:
 // d_params[55169] = pull-back of d_images through the render (jax.value_and_grad, bhnerf/network.py:617,:677)
 static ffi::Error RenderBwdImpl(cudaStream_t stream, ffi::AnyBuffer packed, ffi::Buffer<ffi::F32> params,
                                 ffi::Buffer<ffi::F32> t_frames, ffi::Buffer<ffi::F32> d_images,
-                                ffi::Buffer<ffi::F32> e, ffi::Buffer<ffi::U8> acts, ffi::Span<const float> consts,
+                                ffi::Buffer<ffi::F32> e, ffi::Buffer<ffi::U8> acts, BHNERF_SCENE_ATTR_PARAMS,
                                 ffi::ResultBuffer<ffi::F32> d_params, ffi::ResultBuffer<ffi::U8> workspace) {
-  bhnerf_scene_t sc = scene_of(packed, consts);
+  bhnerf_scene_t sc = scene_of(packed, BHNERF_SCENE_ATTR_VALUES);
   const int32_t Bt = static_cast<int32_t>(t_frames.element_count());
   return to_error(bhnerf_render_bwd(&sc, params.typed_data(), t_frames.typed_data(), Bt, d_images.typed_data(),
                                     e.typed_data(), acts.untyped_data(), d_params->typed_data(),
@@ -56,7 +68,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BhnerfRenderFwd, RenderFwdImpl,
                                   .Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Attr<ffi::Span<const float>>("consts")
+                                  BHNERF_SCENE_ATTR_BINDINGS
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::U8>>()
@@ -71,6 +83,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BhnerfRenderBwd, RenderBwdImpl,
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::U8>>()
-                                  .Attr<ffi::Span<const float>>("consts")
+                                  BHNERF_SCENE_ATTR_BINDINGS
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::U8>>());

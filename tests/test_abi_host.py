@@ -259,3 +259,41 @@ def test_trainstep_eht_reference_signature_with_a_duck_typed_observation(monkeyp
     assert tsc.dtype[0] == 'cphase' and np.allclose(target, np.pi / 2) and np.allclose(sigma, np.pi / 4) and A.shape == (nt, 3, V, P)
     with pytest.raises(AttributeError):
         optimization.TrainStep.eht(t, Obs(), 1e-9, 4, chisqdata_vis, pol='V')
+
+
+def test_jax_ffi_binding_is_self_consistent():
+    """jaxlib is absent, so the jax.ffi binding cannot run here -- but it must be CONSISTENT: the binding
+    parses; every module / name it takes from this repository resolves; the scalar attributes it passes to ffi_call
+    (JaxScene.attrs) are exactly the typed attributes the XLA-FFI shim binds and the fields of bhnerf_scene_t; the targets it
+    registers are the handler symbols the shim defines; the C functions the shim calls are declared in the header."""
+    import ast
+    import re
+    from bhnerf_b200 import _lib, jax_scene
+    src = open(os.path.join(ROOT, 'integration', 'jax_binding.py')).read()
+    tree = ast.parse(src)
+    repo_imports = [n for n in ast.walk(tree) if isinstance(n, ast.ImportFrom) and n.module and n.module.startswith('bhnerf_b200')]
+    assert repo_imports, 'the binding should use bhnerf_b200.jax_scene'
+    import importlib
+    for n in repo_imports:
+        mod = importlib.import_module(n.module)
+        for a in n.names:
+            assert hasattr(mod, a.name), '%s.%s does not exist' % (n.module, a.name)
+    # attributes / methods used on `scene` objects exist on JaxScene
+    used = {n.attr for n in ast.walk(tree) if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == 'scene'}
+    have = set(dir(jax_scene.JaxScene)) | {'P', 'G', 'S', 'n_active', 'n_pad', 'image_shape', 'polarized', 'scene'}
+    assert used and used <= have, used - have
+    shim = open(os.path.join(ROOT, 'integration', 'xla_ffi_shim.cc')).read()
+    bound = re.findall(r'\.Attr<(\w+)>\("(\w+)"\)', shim)
+    want = [('int32_t' if ty == 'int32' else 'float', name) for name, ty in jax_scene.ATTRS]
+    assert bound == want, (bound, want)
+    hdr = open(os.path.join(ROOT, 'include', 'bhnerf_b200.h')).read()
+    struct = re.search(r'typedef struct bhnerf_scene \{(.*?)\} bhnerf_scene_t;', hdr, flags=re.S).group(1)
+    fields = re.findall(r'\b(\w+);', re.sub(r'/\*.*?\*/', '', struct, flags=re.S))
+    assert fields == ['packed'] + [name for name, _ in jax_scene.ATTRS], fields
+    # one Scene field per ctypes field as well
+    assert [f[0] for f in _lib.Scene._fields_] == fields
+    targets = set(re.findall(r"_lib\.(Bhnerf\w+)", src))
+    assert targets == set(re.findall(r'XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),', shim)) and len(targets) == 2
+    for fn in set(re.findall(r'\b(bhnerf_[a-z_]+)\(', shim)):
+        assert fn in _lib.header_functions(), fn
+    assert 'consts' not in shim and 'consts' not in src        # the struct-in-a-float-span attribute is gone

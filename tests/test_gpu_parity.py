@@ -684,3 +684,36 @@ def test_two_rank_nccl_step_matches_oracle():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count('ranks identical: True') == 2
     assert r.stdout.count('ray-sharded') == 3 and 'FAILED' not in r.stdout
+
+
+def test_jax_scene_prepack_attributes_and_sizes():
+    """bhnerf_b200.jax_scene (the repository side of the jax.ffi binding): prepack through ctypes, the typed scalar
+    attributes equal the fields of the C scene struct, and a render driven ONLY by (packed buffer, attrs, size queries) --
+    what an XLA-FFI handler receives -- reproduces the golden images."""
+    import ctypes as C
+    from bhnerf_b200 import _lib, engine, jax_scene, network
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    d = np.load(os.path.join(G, 'case_lc_IQU.npz'))
+    pred = network.NeRF_Predictor(float(d['scale']), float(d['rmin']), float(d['rmax']), float(d['z_width']))
+    cache = {}
+    args = (geo['coords'], geo['Omega'], d['J'], geo['g'], geo['dtau'], geo['Sigma'], float(d['t_start_obs']), geo['t_geos'],
+            float(d['t_injection']), 'hr')
+    sc = jax_scene.prepack(pred, *args, scene_cache=cache)
+    assert jax_scene.prepack(pred, *args, scene_cache=cache) is sc
+    a = sc.attrs
+    assert [k for k in a] == [n for n, _ in jax_scene.ATTRS] and a['P'] == 256 and a['G'] == 32 and a['S'] == 3
+    assert a['n_pad'] % 128 == 0 and 0 < a['n_active'] <= a['n_pad'] and a['scale'].dtype == np.float32
+    Bt = 4
+    assert sc.acts_bytes(Bt) > 0 and sc.fwd_workspace_bytes > 0 and sc.bwd_workspace_bytes(Bt) > sc.bwd_workspace_bytes(1)
+    # what the handler does: rebuild the struct from (buffer pointer, attrs) and call the C ABI
+    st = _lib.Scene(packed=sc.packed.data_ptr(), **{k: (int(v) if np.issubdtype(type(v), np.integer) else float(v)) for k, v in a.items()})
+    lib = _lib.load()
+    dev = sc.packed.device
+    params = torch.as_tensor(d['params_flat'], device=dev); tf = torch.as_tensor(d['t_frames'].astype(np.float32), device=dev)
+    images = torch.empty((Bt, 3, 256), device=dev); e = torch.empty((Bt, int(a['n_pad'])), device=dev)
+    ws = torch.empty(sc.fwd_workspace_bytes, dtype=torch.uint8, device=dev)
+    rc = lib.bhnerf_render_fwd(C.byref(st), params.data_ptr(), tf.data_ptr(), Bt, images.data_ptr(), e.data_ptr(), None,
+                               ws.data_ptr(), ws.numel(), _lib.IMPL_TC, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.bhnerf_last_error()
+    torch.cuda.synchronize()
+    assert np.abs(images.cpu().numpy().reshape(d['images'].shape) - d['images']).max() / np.abs(d['images']).max() < IMG_TOL

@@ -56,6 +56,8 @@ SIGNATURES = {
     'bhnerf_grid_render_bwd': (C.c_int, [_SP, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp]),
     'bhnerf_geodesic_inputs': (C.c_int, [_vp] * 7 + [C.c_int64, _i32, C.c_double, C.c_double, C.c_double, C.c_double]
                                + [_vp] * 7),
+    'bhnerf_polarization_workspace_bytes': (_sz, [C.c_int64, _i32]),
+    'bhnerf_polarization_factors': (C.c_int, [_vp] * 8 + [C.c_int64, _i32] + [C.c_double] * 10 + [_i32, _vp, _vp, _sz, _vp]),
     'bhnerf_adam_step_dev': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _f32, _f32, _i32, _f32, _f32, _f32, _f32, _vp, _vp]),
     'bhnerf_workspace_status': (C.c_int, [_vp, C.POINTER(C.c_int32), _vp]),
     'bhnerf_comm_unique_id': (C.c_int, [_vp]),

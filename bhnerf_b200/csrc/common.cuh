@@ -144,6 +144,7 @@ int bh_simt_bwd(const PackedView& v, const float* params, const float* d_images 
 #define BH_SIMT_WT_FLOATS (3 * 128 * 128)
 
 // TC (tcgen05) family.  `planes` = bf16 planes kept of every saved activation / cotangent (1: hi, 2: hi+lo).
+bool bh_tc_fast();                                          // BHNERF_PRECISION=fast (stated single-product mode)
 int bh_tc_planes(int n_active, int Bt_total);               // precision plan of a step
 int bh_tc_planes_full_loss(int n_active, int Bt_total);     // ... of the fused step with the per-pixel image loss
 size_t bh_tc_acts_bytes_per_frame(int n_pad, int planes);

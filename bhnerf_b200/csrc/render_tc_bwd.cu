@@ -93,7 +93,7 @@ tc_dout_kernel(PackedView v, const float* __restrict__ d_images, const float* e,
 template <int PL, bool FUSED, bool WIDE>
 __device__ __forceinline__ void
 dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, const PackedView& v,
-           const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
+           const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt, const int passes,
            const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
            float* __restrict__ d_params, int* __restrict__ status) {
   uint8_t* wsm = smem + D_SM_W;
@@ -172,7 +172,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
               const uint32_t b_hi = desc_hi(TC_IMG_RS), b_lo0 = desc_lo(wl, cs), b_lo1 = desc_lo(wl + plane, cs);
               const uint32_t kstep = (2u * cs) >> 4;
 #pragma unroll
-              for (int pp = 0; pp < (PL == 2 ? 3 : BH_DGRAD_PASSES); ++pp)
+              for (int pp = 0; pp < (PL == 2 ? 3 : passes); ++pp)
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                   mma_ts_raw(td, ta + (pp == 2 ? 64u : 0u) + (uint32_t)ks * 8u, (pp == 1 ? b_lo1 : b_lo0) + (uint32_t)ks * kstep,
@@ -545,11 +545,11 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 
 template <int PL, bool WIDE>
 __global__ void __launch_bounds__(kDThreads, 1)
-tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
+tc_dgrad_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt, int passes,
                 const uint8_t* __restrict__ acts, uint8_t* __restrict__ deltas,
                 float* __restrict__ d_params, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  dgrad_role<PL, false, WIDE>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, dout_all, Bt, acts,
+  dgrad_role<PL, false, WIDE>(smem, (int)blockIdx.x, (int)gridDim.x, PairLink{nullptr, 0u}, v, ws, dout_all, Bt, passes, acts,
                         deltas, d_params, status);
 }
 
@@ -888,7 +888,7 @@ constexpr uint32_t F_SM_TOTAL = D_SM_TOTAL > WCfg<1>::SM_TOTAL ? D_SM_TOTAL : WC
 // resident); ND = 2 is kept as a measured alternative (see bwd_dgrad_per_cluster).
 template <bool WIDE, int ND>
 __global__ void __cluster_dims__(ND + 1, 1, 1) __launch_bounds__(kDThreads, 1)
-tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt,
+tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* __restrict__ dout_all, int Bt, int passes,
                     const uint8_t* __restrict__ acts, uint8_t* __restrict__ ring,
                     float* __restrict__ d_params, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -898,7 +898,7 @@ tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* _
     PairLink link;
     link.ring = ring + (size_t)(cl * ND + (int)rank) * kRingDepth * TSET_BYTES;
     link.peer_bars = mapa_u32(smem_u32(smem + WCfg<1>::SM_BARS + (WB_GFULL + rank * kRingDepth) * 8), (uint32_t)ND);
-    dgrad_role<1, true, WIDE>(smem, cl * ND + (int)rank, ncl * ND, link, v, ws, dout_all, Bt, acts, nullptr, d_params, status);
+    dgrad_role<1, true, WIDE>(smem, cl * ND + (int)rank, ncl * ND, link, v, ws, dout_all, Bt, passes, acts, nullptr, d_params, status);
   } else {
     PairLink links[ND];
 #pragma unroll
@@ -948,6 +948,8 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
                void* delta_ws, float* dout, float* d_params, cudaStream_t st) {
   int* status = (int*)((uint8_t*)ws + TC_WS_STATUS);
   const int NT = Bt * (v.n_pad / 128);
+  // products per layer of the one-plane chain: d*W_hi + d*W_lo; the stated fast mode (BHNERF_PRECISION=fast) drops W_lo
+  const int dgrad_passes = (PL == 1 && bh_tc_fast()) ? 1 : BH_DGRAD_PASSES;
   {
     BhProfScope ps(BH_CAT_HEADS, 1, st);
     size_t n = (size_t)Bt * v.n_pad;
@@ -980,7 +982,7 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
       if (getenv("BHNERF_DEBUG")) fprintf(stderr, "bhnerf_b200: fused backward, clusters of %d: %d resident at once\n", ndc + 1, n);
     }
     if (ncl > max_cl[ndc]) ncl = max_cl[ndc];
-    kern<<<(ndc + 1) * ncl, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts,
+    kern<<<(ndc + 1) * ncl, kDThreads, F_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, dgrad_passes, (const uint8_t*)acts,
                                                          (uint8_t*)delta_ws, d_params, status);
     BH_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -990,7 +992,7 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
     auto kern = dgrad_wide_enabled() ? tc_dgrad_kernel<PL, true> : tc_dgrad_kernel<PL, false>;
     BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SM_TOTAL));
     int grid = (NT + 1) / 2; if (grid > num_sms_b()) grid = num_sms_b();
-    kern<<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts, (uint8_t*)delta_ws,
+    kern<<<grid, kDThreads, D_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, dgrad_passes, (const uint8_t*)acts, (uint8_t*)delta_ws,
                                               d_params, status);
     BH_CHECK_CUDA(cudaGetLastError());
   }

@@ -92,3 +92,44 @@ def geodesic_inputs(geos, Omega=None, omega_sign=None, fillna=0.0, device=None):
     res = {k: v.reshape(shape) for k, v in out.items()}
     res['coords'] = coords.reshape((3,) + shape)
     return res
+
+
+def polarization_factors(geos, Omega=None, b_consts=None, Q_frac=0.5, rmin=0.0, rmax=np.inf, z_width=np.inf,
+                         spectral_index=1, omega_sign=None, device=None):
+    """The Stokes factors ``J = (I, Q, U)`` of ``network.raytracing_args`` on the GPU (C ABI: bhnerf_polarization_factors):
+    alma.image_plane_model's chain (bhnerf/alma.py:47-60) -- azimuthal_velocity_vector, doppler_factor,
+    magnetic_field_fluid_frame(**b_consts) normalised by its mean strength in the recovery domain, parallel_transport(Q_frac,
+    V_frac=0) (bhnerf/kgeo.py:199-248, 274-313, 438-519), nan_to_num.  ``geos``: mapping / namespace with float64 r, theta,
+    affine of shape (*img, G), per-ray lam, eta, alpha, beta (shape *img or broadcast (*img, G)), spin, inc.
+    ``b_consts`` = dict(arad, avert, ator).  Returns a float32 device tensor (3, *img, G); apply emission.rotate_evpa for
+    the reference's rot_angle."""
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else 'cuda')
+    b_consts = b_consts or dict(arad=0.0, avert=1.0, ator=0.0)
+    f64 = lambda a: torch.as_tensor(np.array(a, dtype=np.float64, order='C'), device=dev)
+    r = _get(geos, 'r')
+    shape = tuple(r.shape)
+    G = shape[-1]
+    P = int(np.prod(shape[:-1]))
+
+    def per_ray(k):
+        v = np.asarray(_get(geos, k), dtype=np.float64)
+        v = np.broadcast_to(v, shape)[..., 0] if v.ndim == len(shape) else np.broadcast_to(v, shape[:-1])
+        return f64(v).reshape(P).contiguous()
+    rr, th, aff = [f64(_get(geos, k)).reshape(P, G).contiguous() for k in ('r', 'theta', 'affine')]
+    lam, eta, alpha, beta = [per_ray(k) for k in ('lam', 'eta', 'alpha', 'beta')]
+    a = float(_get(geos, 'spin')); inc = float(_get(geos, 'inc'))
+    Om_in = None if Omega is None else f64(np.broadcast_to(np.asarray(Omega, dtype=np.float64), shape)).reshape(P, G).contiguous()
+    if omega_sign is None:
+        omega_sign = float(np.sign(a + np.finfo(float).eps))
+    J = torch.empty((3, P, G), dtype=torch.float32, device=dev)
+    nws = lib.bhnerf_polarization_workspace_bytes(P, G)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_polarization_factors(engine._ptr(rr), engine._ptr(th), engine._ptr(aff), engine._ptr(lam),
+                                              engine._ptr(eta), engine._ptr(alpha), engine._ptr(beta), engine._ptr(Om_in), P, G,
+                                              a, inc, float(omega_sign), float(b_consts['arad']), float(b_consts['avert']),
+                                              float(b_consts['ator']), float(Q_frac), float(rmin), float(min(rmax, 1e300)),
+                                              float(min(z_width, 1e300)), int(spectral_index), engine._ptr(J), engine._ptr(ws),
+                                              nws, engine._stream()))
+    return J.reshape((3,) + shape)

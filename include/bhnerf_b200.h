@@ -189,6 +189,20 @@ int bhnerf_geodesic_inputs(const double* r, const double* theta, const double* p
                            float* coords, float* Omega, float* g, float* dtau, float* Sigma,
                            float* t_geos, void* stream);
 
+/* ---- polarization factors (setup, once per (spin, inclination)): J = (I, Q, U) per geodesic sample, the chain of
+ * alma.image_plane_model (bhnerf/alma.py:47-60): kgeo.azimuthal_velocity_vector (bhnerf/kgeo.py:199-223) -> doppler_factor
+ * (:225-248) -> magnetic_field_fluid_frame(arad, avert, ator) (:274-313) normalised by its mean strength inside the recovery
+ * domain (alma.py:55-57) -> parallel_transport(Q_frac, V_frac = 0, spectral_index) (:438-519) -> nan_to_num.  float64
+ * inputs: r, theta, affine [P,G] (tracer output; affine = Geodesics.sig_s), per-ray lam, eta, alpha, beta [P]
+ * (kerr_raytracing_utils.py:264-266), Omega_in [P,G] or NULL (Keplerian, omega_sign = +-1).  J [3,P,G] float32, the `J`
+ * entry of network.raytracing_args (before emission.rotate_evpa).  workspace >= bhnerf_polarization_workspace_bytes. */
+size_t bhnerf_polarization_workspace_bytes(int64_t P, int32_t G);
+int bhnerf_polarization_factors(const double* r, const double* theta, const double* affine, const double* lam,
+                                const double* eta, const double* alpha, const double* beta, const double* Omega_in,
+                                int64_t P, int32_t G, double spin, double inclination, double omega_sign, double arad,
+                                double avert, double ator, double Q_frac, double rmin, double rmax, double z_width,
+                                int32_t spectral_index, float* J, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- optimiser: optax.adam + polynomial_schedule(power=1) applied by
  * TrainState.apply_gradients (bhnerf/network.py:171-182, :621).  grad_scale multiplies the
  * gradient first (1/ndev turns an all-reduce SUM into jax.lax.pmean, network.py:620).

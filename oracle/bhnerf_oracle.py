@@ -439,3 +439,76 @@ def grid_predictor_images(grid, t_frames, rt, predictor, GM_c3=GM_C3_SGRA_HR, dt
         e = _t(J, dtype)[None] * e[:, None]
     g, dtau, Sigma = [_t(rt[k], dtype) for k in ('g', 'dtau', 'Sigma')]
     return (g ** 2 * e * dtau * Sigma).sum(-1)
+
+
+# --------------------------------------------------------------------------------------
+# Polarization factors J = (I, Q, U): alma.image_plane_model's chain (bhnerf/alma.py:47-60) =
+# azimuthal_velocity_vector (kgeo.py:199-223) -> doppler_factor (:225-248) -> magnetic_field_fluid_frame (:274-313,
+# with fluid_frame_tetrad :315-350) -> parallel_transport (:438-519, V_frac = 0), float64.  For a purely azimuthal
+# 4-velocity (u^r = u^theta = 0, u.u = -1) the tetrad of :338-347 collapses to
+#   e_t = -u,  e_r = (0, 1, 0, 0)/sqrt(g_rr),  e_th = (0, 0, 1, 0)/sqrt(g_thth),  e_ph = (u_ph, 0, 0, -u_t)/(sqrt(Delta) sin th)
+# (u_t, u_ph covariant), which is what is written out below; pinned on the reference's own functions in
+# tests/test_oracle.py (oracle/ref_shim.reference_polarization_factors).
+# --------------------------------------------------------------------------------------
+def polarization_factors(geos, Omega, b_consts, Q_frac, rmin, rmax, z_width, spectral_index=1):
+    """geos: dict of float64 arrays (..., G) with r, theta, affine, lam, eta, alpha, beta (per-ray values broadcast) and
+    scalars spin, inc (E = M = 1).  Returns J (3, ..., G) with NaN -> 0 (bhnerf/alma.py:60)."""
+    r, th, aff = [np.asarray(geos[k], dtype=np.float64) for k in ('r', 'theta', 'affine')]
+    lam, eta, alpha, beta = [np.asarray(geos[k], dtype=np.float64) for k in ('lam', 'eta', 'alpha', 'beta')]
+    a, inc = float(geos['spin']), float(geos['inc'])
+    Om = np.asarray(Omega, dtype=np.float64)
+    arad, avert, ator = b_consts['arad'], b_consts['avert'], b_consts['ator']
+    with np.errstate(all='ignore'):
+        sth, cth = np.sin(th), np.cos(th)
+        Delta = r ** 2 + a ** 2 - 2 * r
+        Sigma = r ** 2 + a ** 2 * cth ** 2
+        Xi = (r ** 2 + a ** 2) ** 2 - a ** 2 * Delta * sth ** 2
+        Rpot = (r ** 2 + a ** 2 - a * lam) ** 2 - Delta * (eta + (lam - a) ** 2)
+        Rpot = np.where(np.abs(Rpot) > 1e-10, Rpot, 0.0)
+        Thpot = eta + a ** 2 * cth ** 2 - lam ** 2 / np.tan(th) ** 2
+        # wave vector k_mu (covariant), kgeo.py:91-117; the signs follow the turning points along the ray
+        pm_r = np.sign(np.gradient(r, axis=-1) / np.gradient(aff, axis=-1))
+        pm_th = np.sign(np.gradient(th, axis=-1) / np.gradient(aff, axis=-1))
+        k_t, k_r = -np.ones_like(r), np.sqrt(np.clip(Rpot, 0, None)) * pm_r / Delta
+        k_th, k_ph = np.sqrt(np.clip(Thpot, 0, None)) * pm_th, lam
+        # metric and the azimuthal 4-velocity
+        g_tt, g_rr, g_thth = -(1 - 2 * r / Sigma), Sigma / Delta, Sigma
+        g_phph, g_tph = Xi * sth ** 2 / Sigma, -2 * a * r * sth ** 2 / Sigma
+        ut = 1 / np.sqrt(-(g_tt + 2 * Om * g_tph + g_phph * Om ** 2))
+        uph = ut * Om
+        u_t, u_ph = g_tt * ut + g_tph * uph, g_phph * uph + g_tph * ut          # covariant
+        s = u_t * ut + u_ph * uph                                               # = -1 where the orbit is timelike
+        N_r, N_th, N_ph = np.sqrt(-g_rr * s), np.sqrt(g_thth), np.sqrt(-s * Delta * sth ** 2)
+        gdop = 1.0 / -(k_t * ut + k_ph * uph)                                   # doppler_factor, NaN -> 0 (kgeo.py:246)
+        gdop = np.where(np.isnan(gdop), 0.0, gdop)
+        # k in the fluid frame (spatial part): k'_j = e_j^mu k_mu
+        kp = np.stack([-s * k_r / N_r, k_th / N_th, (u_ph * k_t - u_t * k_ph) / N_ph], axis=-1)
+        # fluid-frame magnetic field (kgeo.py:290-313)
+        Br, Bth, Bph = arad * sth + avert * cth, -avert * sth, ator * np.ones_like(r)
+        b0 = Bph * u_ph
+        b1, b2, b3 = Br / u_t, Bth / u_t, (Bph + b0 * u_ph) / u_t
+        bl = [g_tt * b0 + g_tph * b3, g_rr * b1, g_thth * b2, g_phph * b3 + g_tph * b0]
+        bp = np.stack([-s * bl[1] / N_r, bl[2] / N_th, (u_ph * bl[0] - u_t * bl[3]) / N_ph], axis=-1)
+        z = r * cth
+        domain = (np.abs(z) < z_width) & (r > rmin) & (r < rmax)
+        b_mean = np.sqrt((bp[domain] ** 2).sum(-1)).mean()                      # alma.py:55-57
+        bp = bp / b_mean
+        # parallel_transport (kgeo.py:476-518)
+        k_mag = np.sqrt((kp ** 2).sum(-1))
+        f_loc = np.cross(kp, bp, axis=-1) / k_mag[..., None]
+        f_t, f_r = u_ph / N_ph * f_loc[..., 2], -s / N_r * f_loc[..., 0]
+        f_th, f_ph = f_loc[..., 1] / N_th, -u_t / N_ph * f_loc[..., 2]
+        b_mag = np.sqrt((bp ** 2).sum(-1))
+        sin_b = np.sqrt((f_loc ** 2).sum(-1)) / k_mag
+        I = gdop ** spectral_index * b_mag ** (spectral_index + 1) * sin_b ** (spectral_index + 1)
+        Q = Q_frac * I
+        gi_tt, gi_rr, gi_thth = -Xi / (Delta * Sigma), Delta / Sigma, 1 / Sigma
+        gi_phph, gi_tph = (Delta - a ** 2 * sth ** 2) / (Delta * Sigma * sth ** 2), -2 * a * r / (Delta * Sigma)
+        ku = [gi_tt * k_t + gi_tph * k_ph, gi_rr * k_r, gi_thth * k_th, gi_phph * k_ph + gi_tph * k_t]
+        A = (ku[0] * f_r - ku[1] * f_t) + a * sth ** 2 * (ku[1] * f_ph - ku[3] * f_r)
+        B = ((r ** 2 + a ** 2) * (ku[3] * f_th - ku[2] * f_ph) - a * (ku[0] * f_th - ku[2] * f_t)) * sth
+        kappa = (r - 1j * a * cth) * (A - 1j * B)
+        mu = -(alpha + a * np.sin(inc))
+        chi2 = np.angle(((beta + 1j * mu) * np.conj(kappa)) / ((beta - 1j * mu) * kappa))
+        J = np.stack([I, np.cos(chi2) * Q, np.sin(chi2) * Q])
+    return np.nan_to_num(J, nan=0.0)

@@ -717,3 +717,29 @@ def test_jax_scene_prepack_attributes_and_sizes():
     assert rc == 0, lib.bhnerf_last_error()
     torch.cuda.synchronize()
     assert np.abs(images.cpu().numpy().reshape(d['images'].shape) - d['images']).max() / np.abs(d['images']).max() < IMG_TOL
+
+
+def test_polarization_factors_vs_reference_functions():
+    """bhnerf_polarization_factors (kgeo.polarization_factors) against the output of the reference's own
+    azimuthal_velocity_vector / doppler_factor / magnetic_field_fluid_frame / parallel_transport (tests/golden/pol_factors.npz):
+    float64 arithmetic, float32 result; compared inside the recovery domain (outside it the factors diverge towards the
+    horizon and the prepack culls the samples) and, with a looser bound, wherever the reference is finite."""
+    from bhnerf_b200 import kgeo
+    d = np.load(os.path.join(G, 'pol_factors.npz'))
+    for tag in ('a', 'b'):
+        a, inc, rmin, rmax, zw = d[tag + '_consts']
+        geos = dict(r=d[tag + '_r'], theta=d[tag + '_theta'], affine=d[tag + '_affine'], lam=d[tag + '_lam'], eta=d[tag + '_eta'],
+                    alpha=d[tag + '_alpha'], beta=d[tag + '_beta'], spin=float(a), inc=float(inc))
+        dom = (np.abs(geos['r'] * np.cos(geos['theta'])) < zw) & (geos['r'] > rmin) & (geos['r'] < rmax)
+        for j in (0, 1):
+            b = d['%s_b%d' % (tag, j)]
+            J = kgeo.polarization_factors(geos, None, dict(arad=b[0], avert=b[1], ator=b[2]), 0.5, rmin, rmax, zw).cpu().numpy()
+            ref = d['%s_J%d' % (tag, j)]
+            assert J.shape == ref.shape and J.dtype == np.float32 and np.isfinite(J).all()
+            err = np.abs(J[:, dom] - ref[:, dom]).max() / np.abs(ref[:, dom]).max()
+            sane = np.abs(ref) < 1e4
+            err_all = np.abs(J - ref)[sane].max() / np.abs(ref[sane]).max()
+            print(tag, j, 'in-domain err %.2e  everywhere %.2e' % (err, err_all))
+            assert err < 1e-6 and err_all < 1e-5
+    with pytest.raises(Exception, match='Q_frac'):
+        kgeo.polarization_factors(geos, None, None, 1.5, rmin, rmax, zw)

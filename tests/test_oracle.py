@@ -187,3 +187,44 @@ def test_grid_predictor_oracle_golden_is_reproducible():
     img = O.grid_predictor_images(torch.as_tensor(d['grid'].astype(np.float64)), d['t_frames'], rt, pred).numpy()
     np.testing.assert_allclose(img, d['images'], rtol=1e-10, atol=1e-12)
     assert (img[0] == 0).all() and img[-1].max() > 1.0        # first frame is entirely before injection
+
+
+def _pol_case(d, tag):
+    a, inc, rmin, rmax, zw = d[tag + '_consts']
+    shape = d[tag + '_r'].shape
+    bc = lambda v: np.broadcast_to(d[tag + '_' + v][..., None], shape)
+    geos = dict(r=d[tag + '_r'], theta=d[tag + '_theta'], affine=d[tag + '_affine'], lam=bc('lam'), eta=bc('eta'),
+                alpha=bc('alpha'), beta=bc('beta'), spin=float(a), inc=float(inc), M=1.0)
+    Om = np.sign(a + np.finfo(float).eps) / (geos['r'] ** 1.5 + a)
+    return geos, Om, float(rmin), float(rmax), float(zw)
+
+
+def test_polarization_factors_oracle_vs_reference_functions():
+    """oracle.polarization_factors (restatement of alma.image_plane_model's J chain, bhnerf/alma.py:47-60 +
+    bhnerf/kgeo.py:199-248,274-313,438-519) against the committed output of the reference's OWN functions
+    (tests/golden/pol_factors.npz, made by make_golden_pol.py through the mini-xarray of oracle/ref_shim.py), on real Kerr
+    geodesics of two geometries and two field configurations -- and live against the reference when it is present."""
+    from oracle import bhnerf_oracle as O
+    d = np.load(os.path.join(G, 'pol_factors.npz'))
+    for tag in ('a', 'b'):
+        geos, Om, rmin, rmax, zw = _pol_case(d, tag)
+        dom = (np.abs(geos['r'] * np.cos(geos['theta'])) < zw) & (geos['r'] > rmin) & (geos['r'] < rmax)
+        assert dom.sum() > 100
+        for j in (0, 1):
+            b = d['%s_b%d' % (tag, j)]
+            J = O.polarization_factors(geos, Om, dict(arad=b[0], avert=b[1], ator=b[2]), 0.5, rmin, rmax, zw)
+            ref = d['%s_J%d' % (tag, j)]
+            assert J.shape == ref.shape == (3,) + geos['r'].shape
+            assert np.abs(J[:, dom] - ref[:, dom]).max() / np.abs(ref[:, dom]).max() < 1e-12
+            sane = np.abs(ref) < 1e6                      # near the horizon the factors blow up (and are culled by the domain)
+            assert np.abs(J - ref)[sane].max() / np.abs(ref[sane]).max() < 1e-9
+            assert np.abs(ref[1:, dom]).max() > 0.05 and np.abs(ref[2, dom]).max() > 1e-3     # Q and U are exercised
+    from oracle import ref_shim
+    if ref_shim.available():
+        g = ref_shim.kerr_geodesics(0.5, np.deg2rad(40.0), 20.0, 8, 8, 16)
+        Om = ref_shim.keplerian_omega(g)
+        bcs = dict(arad=0.2, avert=0.7, ator=-0.4)
+        Jr, _ = ref_shim.reference_polarization_factors(g, Om, bcs, 0.3, 4.5, 10.0, 3.0)
+        Jo = O.polarization_factors(g, Om, bcs, 0.3, 4.5, 10.0, 3.0)
+        dom = (np.abs(g['z']) < 3.0) & (g['r'] > 4.5) & (g['r'] < 10.0)
+        assert np.abs(Jr[:, dom] - Jo[:, dom]).max() / np.abs(Jr[:, dom]).max() < 1e-12

@@ -40,6 +40,8 @@ SIGNATURES = {
     'bhnerf_loss_image': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     'bhnerf_vis_fwd': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     'bhnerf_loss_vis': (C.c_int, [_vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    'bhnerf_vis_dft_fwd': (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    'bhnerf_vis_dft_bwd': (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     'bhnerf_vis_head': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     'bhnerf_vis_bwd': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     'bhnerf_train_workspace_bytes': (_sz, [_SP, _i32, _i32]),

@@ -312,6 +312,37 @@ def vis_head(A, images, target, sigma, scale, kind, want_grad=True, group_bytes=
     return loss, vis, dI
 
 
+def vis_dft_fwd(uv, images, grid, pulse=None):
+    """Separable visibility head, forward (C ABI: bhnerf_vis_dft_fwd; tcgen05): vis [Bt,V] complex64 from uv [Bt,V,2] and
+    images [Bt,NA,NB]; grid = (x0, dx, y0, dy) of the pixel centres; pulse [Bt,V] complex64 or None."""
+    lib = _lib.load(); dev = images.device
+    uv = _dev_f32(uv, dev)
+    Bt, V = uv.shape[:2]
+    NA, NB = images.shape[-2:]
+    assert images.numel() == Bt * NA * NB
+    pulse = None if pulse is None else _c64(pulse, dev)
+    vis = torch.empty((Bt, V), dtype=torch.complex64, device=dev)
+    st = torch.zeros(2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_vis_dft_fwd(_ptr(uv), _ptr(pulse), _ptr(images), Bt, V, NA, NB, *[float(v) for v in grid], _ptr(vis),
+                                     _ptr(st), _stream()))
+    return vis
+
+
+def vis_dft_bwd(uv, dvis, grid, NA, NB, pulse=None):
+    """Separable visibility head, pull-back to the images (C ABI: bhnerf_vis_dft_bwd): d_images [Bt,NA,NB]."""
+    lib = _lib.load(); dev = dvis.device
+    uv = _dev_f32(uv, dev)
+    Bt, V = uv.shape[:2]
+    pulse = None if pulse is None else _c64(pulse, dev)
+    dI = torch.empty((Bt, NA, NB), dtype=torch.float32, device=dev)
+    st = torch.zeros(2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.bhnerf_vis_dft_bwd(_ptr(uv), _ptr(pulse), _ptr(dvis), Bt, V, NA, NB, *[float(v) for v in grid], _ptr(dI),
+                                     _ptr(st), _stream()))
+    return dI
+
+
 def vis_bwd(A, dvis, P):
     lib = _lib.load(); dev = dvis.device
     Bt, V = dvis.shape

@@ -126,6 +126,20 @@ int bhnerf_vis_head(const float* A, const float* images, const float* target, co
                     float loss_scale, int32_t kind, int32_t Bt, int32_t rows, int32_t P, float* loss,
                     float* vis, float* d_vis, float* d_images, size_t group_bytes, void* stream);
 
+/* ---- separable visibility head on the tensor cores (opt-in).  ehtim fills the per-frame matrix of loss_fn_eht
+ * (bhnerf/network.py:542-544) with the Fourier kernel of the regular pixel grid,
+ *   A[b,k,(i,j)] = pulse[b,k] * exp(-2 pi i (u[b,k] x_i + v[b,k] y_j)),   x_i = x0 + i dx (alpha axis), y_j = y0 + j dy.
+ * Given (u, v) instead of A, vis = A vec(I) is a GEMM with the DFT factor of one axis (tcgen05, factors generated in shared
+ * memory) and a row-wise contraction with the factor of the other: nothing of size nvis x npix is read.  uv [Bt,V,2] in
+ * cycles per unit of x / y; pulse [Bt,V] complex64 or NULL (1); images / d_images [Bt,NA,NB] (NA, NB <= 128 forward;
+ * NB <= 128 backward); vis / d_vis [Bt,V] complex64.  status_dev: 2 int32 of device scratch (word 0 != 0 after the
+ * kernel = a bounded wait expired).  Same results as bhnerf_vis_fwd / bhnerf_vis_bwd with that A, to 1e-4 / 1e-3.      */
+int bhnerf_vis_dft_fwd(const float* uv, const float* pulse, const float* images, int32_t Bt, int32_t V, int32_t NA,
+                       int32_t NB, float x0, float dx, float y0, float dy, float* vis, int32_t* status_dev, void* stream);
+int bhnerf_vis_dft_bwd(const float* uv, const float* pulse, const float* d_vis, int32_t Bt, int32_t V, int32_t NA,
+                       int32_t NB, float x0, float dx, float y0, float dy, float* d_images, int32_t* status_dev,
+                       void* stream);
+
 /* ---- fused train step for the separable image losses: per frame chunk
  * fwd -> ray integral -> loss -> bwd with activations kept in `workspace`.  Replaces
  * gradient_step_image up to (not including) pmean/apply_gradients (network.py:617-619).

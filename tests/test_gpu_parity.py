@@ -743,3 +743,38 @@ def test_polarization_factors_vs_reference_functions():
             assert err < 1e-6 and err_all < 1e-5
     with pytest.raises(Exception, match='Q_frac'):
         kgeo.polarization_factors(geos, None, None, 1.5, rmin, rmax, zw)
+
+
+@pytest.mark.parametrize('NA,NB,V,Bt', [(16, 16, 20, 3), (128, 128, 190, 4), (96, 80, 130, 2)])
+def test_separable_tensor_core_dft_head_matches_the_explicit_matrix(NA, NB, V, Bt):
+    """bhnerf_vis_dft_fwd / _bwd (tcgen05 GEMM with DFT factors generated on chip from (u, v)) against the explicit-matrix
+    head (bhnerf_vis_fwd / _bwd) fed with A[b,k,(i,j)] = pulse * exp(-2 pi i (u x_i + v y_j)) -- the matrix ehtim builds for
+    loss_fn_eht (bhnerf/network.py:542-544) -- and against float64 numpy.  Visibilities <= 1e-4, pull-back <= 1e-3."""
+    from bhnerf_b200 import engine
+    rng = np.random.default_rng(NA + V)
+    psize = 16.0 / NA
+    x = (np.arange(NA) - NA / 2) * psize; y = (np.arange(NB) - NB / 2) * psize
+    uv = rng.uniform(-0.25, 0.25, size=(Bt, V, 2))
+    pulse = (rng.normal(1, 0.1, (Bt, V)) + 1j * rng.normal(0, 0.1, (Bt, V)))
+    ph = -2 * np.pi * (uv[..., 0][:, :, None, None] * x[None, None, :, None] + uv[..., 1][:, :, None, None] * y[None, None, None, :])
+    A64 = (pulse[:, :, None, None] * np.exp(1j * ph)).reshape(Bt, V, NA * NB)
+    img = rng.uniform(0, 1, size=(Bt, NA, NB)) * np.exp(rng.normal(0, 2, size=(Bt, NA, NB)))      # several decades
+    dv = (rng.normal(0, 1, (Bt, V)) + 1j * rng.normal(0, 1, (Bt, V))) * 3e4                          # sigma = 0.01-sized cotangents
+    vis64 = np.einsum('bkp,bp->bk', A64, img.reshape(Bt, -1))
+    dI64 = np.einsum('bkp,bk->bp', np.conj(A64), dv).real.reshape(Bt, NA, NB)
+    grid = (x[0], psize, y[0], psize)
+    img_d = torch.as_tensor(img.astype(np.float32)).cuda()
+    vis = engine.vis_dft_fwd(uv.astype(np.float32), img_d, grid, pulse=pulse.astype(np.complex64))
+    dI = engine.vis_dft_bwd(uv.astype(np.float32), torch.as_tensor(dv.astype(np.complex64)).cuda(), grid, NA, NB,
+                            pulse=pulse.astype(np.complex64))
+    A_d = torch.as_tensor(A64.astype(np.complex64)).cuda()
+    vis_x = engine.vis_fwd(A_d, img_d.reshape(Bt, 1, -1))
+    dI_x = engine.vis_bwd(A_d, torch.as_tensor(dv.astype(np.complex64)).cuda(), NA * NB)
+    torch.cuda.synchronize()
+    ev = np.abs(vis.cpu().numpy() - vis64).max() / np.abs(vis64).max()
+    ed = np.abs(dI.cpu().numpy() - dI64).max() / np.abs(dI64).max()
+    ev_x = np.abs(vis_x.cpu().numpy() - vis64).max() / np.abs(vis64).max()
+    ed_x = np.abs(dI_x.cpu().numpy().reshape(Bt, NA, NB) - dI64).max() / np.abs(dI64).max()
+    print('separable: vis %.2e dI %.2e   explicit A: vis %.2e dI %.2e' % (ev, ed, ev_x, ed_x))
+    assert ev < IMG_TOL and ev_x < IMG_TOL
+    assert ed < GRAD_TOL and ed_x < GRAD_TOL

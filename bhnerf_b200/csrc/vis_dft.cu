@@ -8,7 +8,8 @@
 //   backward  G[k,i] = conj(pulse_k E_u[k,i]) d_vis_k;   d_I[i,j] = sum_k Re(G[k,i] conj(E_v[k,j]))   -- GEMM  (M = i, N = j, K = k)
 // The DFT factors are generated in shared memory from (u, v) -- nothing of size V x P is ever read: 1.5 KB of (u, v) per frame
 // instead of 25 MB of A.  tcgen05.mma kind::f16, fp32 accumulate in TMEM; the images / cotangents go in as fp16 hi + lo
-// planes (22 bits), the unit-modulus factors as one fp16 plane (2^-12 absolute, random over the contraction).
+// planes (22 bits) and so do the unit-modulus factors (with one fp16 plane their 2^-12 error showed up at 1.5e-4 of the
+// visibilities of a 16 x 16 image with a few dominant pixels); three products per accumulator, hi*hi + hi*lo + lo*hi.
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
 
@@ -19,12 +20,20 @@ namespace {
 constexpr int kDftThreads = 128;         // 4 warps: one TMEM lane quadrant each; thread = one GEMM row
 // shared memory: operand images of 128 rows x 128 columns fp16 (32 KB each, the canonical layout of tc_common.cuh)
 constexpr uint32_t DF_IMG = TC_SIMG_BYTES;
-constexpr uint32_t DF_SM_A0 = 0, DF_SM_A1 = DF_IMG, DF_SM_B0 = 2 * DF_IMG, DF_SM_B1 = 3 * DF_IMG;
-constexpr uint32_t DF_SM_BARS = 4 * DF_IMG;
+constexpr uint32_t DF_SM_A0 = 0, DF_SM_A1 = DF_IMG, DF_SM_B0 = 2 * DF_IMG, DF_SM_B1 = 3 * DF_IMG, DF_SM_A2 = 4 * DF_IMG,
+                   DF_SM_A3 = 5 * DF_IMG;
+constexpr uint32_t DF_SM_BARS = 6 * DF_IMG;
 constexpr uint32_t DF_SM_TOTAL = DF_SM_BARS + 64;
 
 __device__ __forceinline__ void store_h(uint8_t* img, int row, int col, float v) {
   *reinterpret_cast<__half*>(img + sample_img_off(row, col >> 3) + (uint32_t)(col & 7) * 2u) = __float2half_rn(v);
+}
+// fp16 hi / lo planes of v (22 significant bits) into two images
+__device__ __forceinline__ void store_h2(uint8_t* img_hi, uint8_t* img_lo, int row, int col, float v) {
+  const __half h = __float2half_rn(v);
+  const uint32_t off = sample_img_off(row, col >> 3) + (uint32_t)(col & 7) * 2u;
+  *reinterpret_cast<__half*>(img_hi + off) = h;
+  *reinterpret_cast<__half*>(img_lo + off) = __float2half_rn(v - __half2float(h));
 }
 
 struct DftGrid { float x0, dx, y0, dy; int NA, NB; };
@@ -48,8 +57,8 @@ vis_dft_fwd_kernel(const float2* __restrict__ uv, const float2* __restrict__ pul
   for (int j = 0; j < 128; ++j) {
     float sn = 0.f, cs = 0.f;
     if (j < g.NB) sincospif(2.f * uvk.y * (g.y0 + j * g.dy), &sn, &cs);
-    store_h(smem + DF_SM_A0, tid, j, j < g.NB ? cs : 0.f);
-    store_h(smem + DF_SM_A1, tid, j, j < g.NB ? sn : 0.f);
+    store_h2(smem + DF_SM_A0, smem + DF_SM_A2, tid, j, j < g.NB ? cs : 0.f);       // C hi | C lo
+    store_h2(smem + DF_SM_A1, smem + DF_SM_A3, tid, j, j < g.NB ? sn : 0.f);       // S hi | S lo
   }
   for (int idx = tid; idx < 128 * 128; idx += kDftThreads) {       // coalesced over j
     const int i = idx >> 7, j = idx & 127;
@@ -68,13 +77,16 @@ vis_dft_fwd_kernel(const float2* __restrict__ uv, const float2* __restrict__ pul
       const uint32_t idesc = make_idesc_f16(128, 128, 0, 0);
       const uint32_t hi = desc_hi(TC_IMG_RS), kstep = (2u * TC_SIMG_CS) >> 4;
       const uint32_t a0 = desc_lo(smem_u32(smem + DF_SM_A0), TC_SIMG_CS), a1 = desc_lo(smem_u32(smem + DF_SM_A1), TC_SIMG_CS);
+      const uint32_t a2 = desc_lo(smem_u32(smem + DF_SM_A2), TC_SIMG_CS), a3 = desc_lo(smem_u32(smem + DF_SM_A3), TC_SIMG_CS);
       const uint32_t b0 = desc_lo(smem_u32(smem + DF_SM_B0), TC_SIMG_CS), b1 = desc_lo(smem_u32(smem + DF_SM_B1), TC_SIMG_CS);
 #pragma unroll
-      for (uint32_t ks = 0; ks < 8; ++ks) {
+      for (uint32_t ks = 0; ks < 8; ++ks) {      // hi*hi + hi*lo + lo*hi per accumulator
         mma_ss_raw(tbase, a0 + ks * kstep, hi, b0 + ks * kstep, hi, idesc, ks ? 1u : 0u);
         mma_ss_raw(tbase, a0 + ks * kstep, hi, b1 + ks * kstep, hi, idesc, 1u);
+        mma_ss_raw(tbase, a2 + ks * kstep, hi, b0 + ks * kstep, hi, idesc, 1u);
         mma_ss_raw(tbase + 128u, a1 + ks * kstep, hi, b0 + ks * kstep, hi, idesc, ks ? 1u : 0u);
         mma_ss_raw(tbase + 128u, a1 + ks * kstep, hi, b1 + ks * kstep, hi, idesc, 1u);
+        mma_ss_raw(tbase + 128u, a3 + ks * kstep, hi, b0 + ks * kstep, hi, idesc, 1u);
       }
       mma_commit_raw(bar);
     }
@@ -159,7 +171,7 @@ vis_dft_bwd_kernel(const float2* __restrict__ uv, const float2* __restrict__ pul
         for (int j = 0; j < 128; ++j) {
           float sn = 0.f, cs = 0.f;
           if (k < V && j < g.NB) sincospif(2.f * vk * (g.y0 + j * g.dy), &sn, &cs);
-          store_h(smem + DF_SM_B0, tid, j, chain == 0 ? cs : sn);
+          store_h2(smem + DF_SM_B0, smem + DF_SM_B1, tid, j, chain == 0 ? cs : sn);
         }
       }
       fence_proxy_async_smem();
@@ -170,11 +182,12 @@ vis_dft_bwd_kernel(const float2* __restrict__ uv, const float2* __restrict__ pul
           const uint32_t a_hi = desc_hi(TC_IMG_RS), akstep = (2u * TC_SIMG_CS) >> 4;
           const uint32_t b_hi = desc_hi(TC_SIMG_CS), bkstep = (2u * TC_IMG_RS) >> 4;
           const uint32_t a0 = desc_lo(smem_u32(smem + DF_SM_A0), TC_SIMG_CS), a1 = desc_lo(smem_u32(smem + DF_SM_A1), TC_SIMG_CS);
-          const uint32_t b0 = desc_lo(smem_u32(smem + DF_SM_B0), TC_IMG_RS);
+          const uint32_t b0 = desc_lo(smem_u32(smem + DF_SM_B0), TC_IMG_RS), b1 = desc_lo(smem_u32(smem + DF_SM_B1), TC_IMG_RS);
 #pragma unroll
           for (uint32_t ks = 0; ks < 8; ++ks) {
             mma_ss_raw(tbase, a0 + ks * akstep, a_hi, b0 + ks * bkstep, b_hi, idesc, (started | ks) ? 1u : 0u);
             mma_ss_raw(tbase, a1 + ks * akstep, a_hi, b0 + ks * bkstep, b_hi, idesc, 1u);
+            mma_ss_raw(tbase, a0 + ks * akstep, a_hi, b1 + ks * bkstep, b_hi, idesc, 1u);
           }
           mma_commit_raw(bar);
         }

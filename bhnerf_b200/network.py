@@ -359,6 +359,64 @@ def loss_fn_image(params, predictor_fn, target, sigma, offset, t_frames, coords,
     return loss, [_shape_images(images, scene, J)]
 
 
+class SeparableDFT(object):
+    """Opt-in stand-in for the explicit matrix ``A`` of loss_fn_eht (network.py:542-544) when it is the plain Fourier kernel
+    of the pixel grid, ``A[..., k, (i,j)] = pulse_k exp(-2 pi i (u_k x_i + v_k y_j))`` -- what ehtim's chisqdata_* build.
+    Holds the baselines instead of the matrix: ``uv`` with the shape of ``A`` minus the pixel axis plus a trailing 2
+    ((nt, [npol,] [3,] nvis, 2), cycles per unit of x / y), the pixel grid ``x_i = x0 + i dx`` (alpha axis), ``y_j = y0 + j dy``
+    and an optional complex ``pulse`` factor per visibility.  The eht steps then run the separable tensor-core head
+    (bhnerf_vis_dft_fwd / _bwd) and never touch anything of size nvis x npix."""
+
+    def __init__(self, uv, image_shape, x0, dx, y0, dy, pulse=None):
+        self.uv = np.ascontiguousarray(np.asarray(uv, dtype=np.float32))
+        assert self.uv.shape[-1] == 2
+        self.image_shape = tuple(int(v) for v in image_shape)
+        self.grid = (float(x0), float(dx), float(y0), float(dy))
+        self.pulse = None if pulse is None else np.ascontiguousarray(np.asarray(pulse, dtype=np.complex64))
+        assert self.pulse is None or self.pulse.shape == self.uv.shape[:-1]
+
+    @classmethod
+    def from_fov(cls, uv, image_shape, fov, pulse=None):
+        """Pixel centres (arange(n) - n/2) * fov/n on both axes (the convention of the synthetic configs)."""
+        NA, NB = image_shape
+        return cls(uv, image_shape, -0.5 * fov, fov / NA, -0.5 * fov, fov / NB, pulse)
+
+    @property
+    def shape(self):                          # the shape the explicit A would have
+        return self.uv.shape[:-1] + (self.image_shape[0] * self.image_shape[1],)
+
+    def dim(self):
+        return len(self.shape)
+
+    def __getitem__(self, key):               # frame indexing only (TemporalBatchedArgs, chunking)
+        if isinstance(key, tuple):
+            assert all(k is Ellipsis for k in key[1:]), 'a SeparableDFT is indexed along its frame axis only'
+            key = key[0]
+        return SeparableDFT(self.uv[key], self.image_shape, *self.grid,
+                            pulse=None if self.pulse is None else self.pulse[key])
+
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else shape
+        assert shape[-1] == self.shape[-1]
+        return SeparableDFT(self.uv.reshape(tuple(shape[:-1]) + (2,)), self.image_shape, *self.grid,
+                            pulse=None if self.pulse is None else self.pulse.reshape(tuple(shape[:-1])))
+
+    def contiguous(self):
+        return self
+
+
+def _vis_head(A, images, target, sigma, scale, dtype, want_grad=True):
+    """(loss[1], vis, d_images | None) of the eht head for an explicit matrix (bhnerf_vis_head) or a SeparableDFT."""
+    if not isinstance(A, SeparableDFT):
+        return engine.vis_head(A, images, target, sigma, scale, dtype, want_grad=want_grad)
+    n = A.shape[0]
+    NA, NB = A.image_shape
+    vis = engine.vis_dft_fwd(A.uv, images.reshape(n, NA, NB), A.grid, pulse=A.pulse)
+    loss, dvis = engine.loss_vis(vis, target, sigma, scale, dtype)
+    dI = engine.vis_dft_bwd(A.uv, dvis, A.grid, NA, NB, pulse=A.pulse).reshape(n, 1, NA * NB) if want_grad else None
+    return loss, vis, dI
+
+
 def _eht_prepare(scene, target, sigma, A, dtype, Bt):
     """Shape checks of loss_fn_eht (network.py:542-559) and the flattening the C ABI takes.  The reference multiplies
     ``A (nt, [npol,] nvis, npix)`` with the image vectors ``(nt, [npol,] npix, 1)`` -- one DFT matrix per frame AND
@@ -366,7 +424,11 @@ def _eht_prepare(scene, target, sigma, A, dtype, Bt):
     returns A as (nt*S, rows, npix) with rows = nvis ('vis','amp') or 3*ncphase ('cphase')."""
     if dtype not in ('vis', 'amp', 'cphase'):
         raise AttributeError('eht dtype ({}) not supported'.format(dtype))
-    A = engine._c64(A, scene.device)
+    if isinstance(A, SeparableDFT):
+        if tuple(A.image_shape) != tuple(scene.image_shape):
+            raise AttributeError('SeparableDFT image_shape {} does not match the rays {}'.format(A.image_shape, scene.image_shape))
+    else:
+        A = engine._c64(A, scene.device)
     tshape = tuple(np.shape(target)) if not isinstance(target, torch.Tensor) else tuple(target.shape)
     S = scene.S
     pol = scene.polarized and not (S == 1 and A.dim() == (4 if dtype == 'cphase' else 3))
@@ -413,8 +475,8 @@ def loss_fn_eht(params, predictor_fn, target, sigma, A, t_frames, coords, Omega,
     images, _, _ = pred._render_fwd(scene, _flat(params, scene.device, pred), tf, impl)
     n = A.shape[0]                                           # frames x polarizations
     tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
-    loss, _, _ = engine.vis_head(A, images.reshape(n, 1, scene.P), _eht_rows(tgt, n),
-                                 _eht_rows(_eht_sigma(sigma, tgt, scene.device), n), float(scale), dtype, want_grad=False)
+    loss, _, _ = _vis_head(A, images.reshape(n, 1, scene.P), _eht_rows(tgt, n),
+                           _eht_rows(_eht_sigma(sigma, tgt, scene.device), n), float(scale), dtype, want_grad=False)
     return loss, [_shape_images(images, scene, J)]
 
 
@@ -695,7 +757,7 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
         rows = slice(b0 * npol, min(b0 + Bc, Bt) * npol)
         images, e, acts = pred._render_fwd(scene, state.flat, tf[sl], impl, save_acts=not isinstance(pred, GRID_Predictor))
         A_c = A[rows].contiguous()
-        l, _, dI = engine.vis_head(A_c, images.reshape(A_c.shape[0], 1, scene.P), tgt[rows], sig[rows], float(scale), dtype)
+        l, _, dI = _vis_head(A_c, images.reshape(A_c.shape[0], 1, scene.P), tgt[rows], sig[rows], float(scale), dtype)
         dI = dI.reshape(images.shape)
         g = pred._render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)
         loss = l if loss is None else engine.add_inplace(loss, l)       # per-chunk partials accumulate on the device

@@ -227,7 +227,9 @@ class TrainStep(object):
             if dtype != 'cphase':
                 raise AttributeError('degrees=True only applies to closure phases (dtype=cphase)')
             target, sigma = np.deg2rad(target), np.deg2rad(sigma).astype(np.float32)
-        args = TemporalBatchedArgs(t_frames, [target, sigma, np.asarray(A, dtype=np.complex64)])
+        if not isinstance(A, network.SeparableDFT):        # opt-in: baselines instead of the matrix (tensor-core DFT head)
+            A = np.asarray(A, dtype=np.complex64)
+        args = TemporalBatchedArgs(t_frames, [target, sigma, A])
         return cls(dtype, args, network.gradient_step_eht, network.test_eht, scale)
 
     @property

@@ -778,3 +778,42 @@ def test_separable_tensor_core_dft_head_matches_the_explicit_matrix(NA, NB, V, B
     print('separable: vis %.2e dI %.2e   explicit A: vis %.2e dI %.2e' % (ev, ed, ev_x, ed_x))
     assert ev < IMG_TOL and ev_x < IMG_TOL
     assert ed < GRAD_TOL and ed_x < GRAD_TOL
+
+
+@pytest.mark.parametrize('dtype', ['vis', 'amp', 'cphase'])
+def test_eht_step_with_separable_dft_equals_the_explicit_matrix_step(dtype):
+    """network.SeparableDFT (baselines instead of the matrix) through TrainStep.eht_arrays -> gradient_step_eht: same loss,
+    images and parameter update as the explicit-A step on the matrix built from the same baselines."""
+    from collections import OrderedDict
+    from bhnerf_b200 import network, optimization
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    d = np.load(os.path.join(G, 'case_vis.npz'))
+    rng = np.random.default_rng(5)
+    nt, NA, NB, V = 4, 16, 16, 15
+    fov = float(geo['fov_M'])
+    x = (np.arange(NA) - NA / 2) * fov / NA
+    lead = (nt, 3, V) if dtype == 'cphase' else (nt, V)
+    uv = rng.uniform(-0.25, 0.25, size=lead + (2,))
+    if dtype == 'cphase':
+        uv[:, 2] = -(uv[:, 0] + uv[:, 1])
+    A = np.exp(-2j * np.pi * (uv[..., 0][..., None, None] * x[:, None] + uv[..., 1][..., None, None] * x[None, :])).reshape(lead + (NA * NB,))
+    tshape = (nt, V)
+    if dtype == 'vis':
+        target = (rng.normal(0, 1, tshape) + 1j * rng.normal(0, 1, tshape)).astype(np.complex64)
+    elif dtype == 'amp':
+        target = np.abs(rng.normal(0.5, 0.3, tshape)).astype(np.float32)
+    else:
+        target = rng.uniform(-np.pi, np.pi, tshape).astype(np.float32)
+    sigma = np.full(tshape, 0.3, dtype=np.float32)
+    pred = network.NeRF_Predictor(float(d['scale']), float(d['rmin']), float(d['rmax']), float(d['z_width']))
+    rt = OrderedDict(coords=geo['coords'], Omega=geo['Omega'], J=1.0, g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
+                     t_start_obs=float(d['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d['t_injection']))
+    out = []
+    for Aarg in (A.astype(np.complex64), network.SeparableDFT.from_fov(uv, (NA, NB), fov)):
+        state = pred.init_state(network.unflatten_params(d['params_flat']), num_iters=100, lr_init=1e-3, lr_final=1e-5)
+        ts = optimization.TrainStep.eht_arrays(d['t_frames'], target, sigma, Aarg, dtype=dtype)
+        loss, state, images = ts(state, rt, np.arange(nt))
+        out.append((loss.item(), images.cpu().numpy(), state.flat.cpu().numpy() - d['params_flat']))
+    assert abs(out[0][0] - out[1][0]) / abs(out[0][0]) < IMG_TOL
+    assert np.abs(out[0][1] - out[1][1]).max() / np.abs(out[0][1]).max() < IMG_TOL
+    assert np.abs(out[0][2] - out[1][2]).max() / 1e-3 < 2e-2            # Adam update ~ lr per parameter

@@ -687,15 +687,14 @@ int launch_fwd(const PackedView& v, const FrameConsts& fc, const void* ws, const
 
 size_t bh_tc_acts_bytes_per_frame(int n_pad, int planes) { return tc_acts_bytes_per_frame(n_pad, planes); }
 
-// Precision plan of the backward: the saved activations / cotangents are bf16.  With the hi plane
-// only, the rounding noise of the wgrad reduction averages out as 1/sqrt(#sample-frames) (measured 1e-4 of the
-// gradient at 4.5e6 sample-frames); below 2^20 sample-frames per step both planes are kept (x3 products, error
-// ~1e-5 at any size).  BHNERF_TC_PLANES=1|2 overrides.
-// Per-pixel image loss ('full'): every pixel's residual enters the gradient with its own sign-stable weight, there is
-// no cancellation between rays, and the one-plane noise is 3.0e-4 of the gradient already at 1.1e4 sample-frames
-// (6e-5 at 5.9e4; scripts/planes_study.py) -- against 6e-3 / 2e-3 for the lightcurve and closure-phase losses, whose
-// gradients are small differences of large per-ray terms.  The fused image step may therefore drop to one plane 16x
-// earlier for 'full'.
+// Precision plan of the backward.  One-plane plan: the saved activations are the forward's fp16 hi plane and
+// the cotangents one fp16 plane (launch-wide power-of-two scale); the rounding noise of the wgrad reduction averages out as
+// 1/sqrt(#sample-frames).  Measured against the float64 oracle at 1.1e4 sample-frames (profiles/r2_planes_fp16.log): 4.9e-4
+// of the gradient for the Q/U lightcurve loss, 2.9e-4 for closure phases (both are small differences of large per-ray terms),
+// 3e-5 .. 5e-5 for the other losses; at 4.5e6 sample-frames 9.6e-5 (that floor is the forward's own 3e-6 image error).  The
+// plan is used from 2^16 sample-frames per step on (worst case 2e-4 there, tolerance 1e-3); below that both bf16 planes are
+// kept (x3 products, two kernels, ~1e-5 at any size).  The per-pixel 'full' loss has no cancellation between rays (2.8e-5 at
+// 1.1e4) and switches at 2^15.  BHNERF_TC_PLANES=1|2 overrides.
 int bh_tc_planes_full_loss(int n_active, int Bt_total) {
   int base = bh_tc_planes(n_active, Bt_total);
   if (base == 1) return 1;
@@ -710,8 +709,7 @@ int bh_tc_planes(int n_active, int Bt_total) {
     forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
   }
   if (forced) return forced;
-  // 2^20: the worst measured case (Q/U lightcurve golden, 6.0e-3 at 1.1e4 sample-frames) scales to 6e-4 there
-  return ((long long)n_active * (long long)Bt_total < (1ll << 20)) ? 2 : 1;
+  return ((long long)n_active * (long long)Bt_total < (1ll << 16)) ? 2 : 1;
 }
 size_t bh_tc_ws_bytes() { return 1u << 20; }
 

@@ -33,6 +33,15 @@ DEFAULT_IMPL = IMPL_TC     # tcgen05 family (parity-green on B200); 'simt' selec
 DEFAULT_MAX_WORKSPACE = int(float(os.environ.get('BHNERF_MAX_WORKSPACE_GB', '40')) * 2 ** 30)
 
 
+def set_max_workspace(nbytes):
+    """Cap (bytes) of the activation workspace used when a call does not pass `max_workspace` itself.  The default, 40 GB of
+    the B200's 180 GB (or BHNERF_MAX_WORKSPACE_GB), lets a full cfg2 step run as one chunk; a smaller cap only changes how
+    many frames a chunk holds, never the result (tests/test_gpu_parity.py: frame chunking)."""
+    global DEFAULT_MAX_WORKSPACE
+    DEFAULT_MAX_WORKSPACE = int(nbytes)
+    return DEFAULT_MAX_WORKSPACE
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

@@ -24,14 +24,14 @@
 extern "C" {
 #endif
 
-#define BHNERF_ABI_VERSION 1
+#define BHNERF_ABI_VERSION 2
 #define BHNERF_N_PARAMS 55169      /* 21x128+128, 128x128+128 (x2), 149x128+128, 128x1+1 */
 #define BHNERF_N_FEAT 21
 #define BHNERF_WIDTH 128
 
 /* which kernel family runs the MLP */
 #define BHNERF_IMPL_SIMT 0         /* fp32 FFMA reference kernels (CUDA cores)              */
-#define BHNERF_IMPL_TC   1         /* tcgen05 tensor cores, bf16x3 split operands, fp32 acc */
+#define BHNERF_IMPL_TC   1         /* tcgen05 tensor cores, fp16 x3 split operands, fp32 acc */
 
 /* loss kinds: bhnerf/network.py:476-484 ('full','lc') and :542-564 ('vis','amp','cphase') */
 #define BHNERF_LOSS_FULL 0
@@ -77,9 +77,10 @@ int bhnerf_prepack(const float* coords, const float* Omega, const float* g, cons
  * MLP :18-64, sigmoid(o-10) :230, masks :231-232) + kgeo.radiative_trasfer (kgeo.py:595-622).
  * images [Bt,S,P] (overwritten).  e_out [Bt,n_pad] (required): per-sample masked emission, the
  * residual the backward needs.  acts_out or NULL: saved activations for the backward
- * (bhnerf_acts_bytes(scene,Bt,impl) bytes; bf16 tiles for TC, fp32 rows for SIMT).           */
+ * (bhnerf_acts_bytes(scene,Bt,impl) bytes; fp16 (one-plane plan) or bf16 hi+lo tiles for TC,
+ * fp32 rows for SIMT).                                                                       */
 size_t bhnerf_acts_bytes(const bhnerf_scene_t* scene, int32_t Bt, int32_t impl);
-size_t bhnerf_fwd_workspace_bytes(int32_t impl);   /* bf16 weight images of the TC family; 0 for SIMT */
+size_t bhnerf_fwd_workspace_bytes(int32_t impl);   /* fp16 / bf16 weight images + status words of the TC family; 0 for SIMT */
 int bhnerf_render_fwd(const bhnerf_scene_t* scene, const float* params, const float* t_frames,
                       int32_t Bt, float* images, float* e_out, void* acts_out, void* workspace,
                       size_t workspace_bytes, int32_t impl, void* stream);

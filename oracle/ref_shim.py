@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY, and usable only in the build container: /root/reference does not
 exist on the GPU box.  Used by ``tests/golden/make_golden.py`` to generate the committed golden
-vectors and by ``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent).
+vectors (``make_golden*.py``) and by the live-reference checks of ``tests/test_oracle.py`` (skipped when the reference is
+absent).
 
 jax / flax / astropy / xarray / kgeo's plotting deps are not installed, so:
   * ``bhnerf/{utils,constants,emission,kgeo}.py`` are loaded by path with ``jax.numpy`` aliased

@@ -17,7 +17,7 @@ def test_library_builds_and_exports_every_declared_symbol(built_lib):
     assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(built_lib, name), name
-    assert built_lib.bhnerf_version() == 1
+    assert built_lib.bhnerf_version() == 2
     # nm view: every declared function is an exported text symbol
     out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
     for name in declared:

@@ -65,6 +65,56 @@ extern "C" int dsmem_bw_run(int mode, int nthreads, int reps, int chunk, long lo
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
+// Are the two ways out of an SM independent?  CTA 0 of every pair pushes `reps` x 32 KB into its partner's shared memory
+// (flags & 1: cp.async.bulk smem -> dsmem) and/or the same amount into an L2-resident global region (flags & 2:
+// cp.async.bulk smem -> global), from two different threads.  out[4*pair + 0/1] = cycles until the DSMEM bytes have
+// landed / until the global copies have completed.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+egress2_kernel(int flags, int reps, uint8_t* __restrict__ gbuf, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];      // [0,64K) source | [64K,128K) destination window
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  for (int i = tid; i < 128 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(i, 1u, 2u, 3u);
+  fence_proxy_async_smem();
+  __syncthreads();
+  cluster_sync_all();
+  const uint32_t dst_remote = mapa(smem_u32(smem + 64 * 1024), rank ^ 1u);
+  const uint32_t bar_remote = mapa(smem_u32(&bar), rank ^ 1u);
+  const long long t0 = clock64();
+  if (rank == 0) {
+    if ((flags & 1) && tid == 0) {
+      for (int r = 0; r < reps; ++r)
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dst_remote + (uint32_t)((r & 1) * 32 * 1024)), "r"(smem_u32(smem) + (uint32_t)((r & 1) * 32768)), "r"(32768), "r"(bar_remote) : "memory");
+    }
+    if ((flags & 2) && tid == 32) {
+      uint8_t* mine = gbuf + (size_t)pair * 262144u;
+      for (int r = 0; r < reps; ++r) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + (size_t)(r & 7) * 32768), "r"(smem_u32(smem) + (uint32_t)((r & 1) * 32768)), "r"(32768u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      out[4 * pair + 1] = clock64() - t0;
+    }
+  } else if ((flags & 1) && tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(reps * 32 * 1024));
+    if (!mbar_wait(&bar, 0, 1u << 24)) out[4 * pair + 2] = -1;
+    out[4 * pair + 0] = clock64() - t0;
+  }
+  cluster_sync_all();
+}
+
+extern "C" int egress2_run(int flags, int reps, int npairs, uint8_t* gbuf, long long* out_dev, void* stream) {
+  size_t smem = 128 * 1024;
+  if (cudaFuncSetAttribute(egress2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+  egress2_kernel<<<2 * npairs, 128, smem, (cudaStream_t)stream>>>(flags, reps, gbuf, out_dev);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
 // D[128 x 64] = A[128 x 64] (bf16, smem K-major) * B[64 x 64] (fp16, smem MN-major), one CTA
 __global__ void __launch_bounds__(128, 1)
 mixed_fmt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int a_fmt, int b_fmt,

@@ -207,3 +207,103 @@ extern "C" int epi_full_run(int flags, uint8_t* gbuf, size_t gbytes, int iters, 
   }
   return (int)cudaGetLastError();
 }
+
+// =====================================================================================================
+// SM egress probe: how many bytes per clock can ONE SM push to an L2-resident region (the cotangent ring of the fused
+// backward: 264 KB per round per dgrad CTA), with 16-byte st.global from all warps (mode 0), with cp.async.bulk
+// shared -> global issued by one thread (mode 1: one 32 KB copy in flight at a time, mode 2: four in flight), and both at
+// once (mode 3)?  Every CTA owns a private 256 KB region (148 x 256 KB = 38 MB: L2 resident).
+// =====================================================================================================
+__global__ void __launch_bounds__(512, 1) egress_kernel(uint8_t* __restrict__ gbuf, int iters, int mode, long long* __restrict__ cycles,
+                                                        long long* __restrict__ bytes) {
+  extern __shared__ __align__(1024) uint8_t esm[];
+  const int tid = threadIdx.x;
+  uint8_t* mine = gbuf + (size_t)blockIdx.x * 262144u;
+  for (int i = tid; i < 131072 / 16; i += 512) reinterpret_cast<uint4*>(esm)[i] = make_uint4(i, tid, 3u, 4u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const long long t0 = clock64();
+  long long nb = 0;
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0 || mode == 3) {          // 512 threads x 16 B x 16 = 128 KB per iteration
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k)
+        *reinterpret_cast<uint4*>(mine + ((size_t)(k * 512 + tid) * 16u)) = make_uint4(it, k, tid, 7u);
+      nb += 131072;
+    }
+    if ((mode == 1 || mode == 3) && tid == 0) {
+      for (int k = 0; k < 4; ++k) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + 131072 + k * 32768), "r"(smem_u32(esm + k * 32768)), "r"(32768u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      nb += 131072;
+    }
+    if (mode == 2 && tid == 0) {
+      for (int k = 0; k < 4; ++k) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + 131072 + k * 32768), "r"(smem_u32(esm + k * 32768)), "r"(32768u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      nb += 131072;
+    }
+    if (mode == 4 && tid < 32) {            // 8 x 16 KB copies issued by 8 lanes
+      if (tid < 8) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + 131072 + tid * 16384), "r"(smem_u32(esm + tid * 16384)), "r"(16384u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      nb += 131072;
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __threadfence();
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) { cycles[blockIdx.x] = t1 - t0; bytes[blockIdx.x] = nb; }
+}
+
+// SM ingress: cp.async.bulk global -> shared, four 32 KB copies in flight, from an L2-resident private region (mode 0)
+// or streaming through a large buffer (mode 1: every CTA walks its own slice of `gbytes`, HBM).
+__global__ void __launch_bounds__(128, 1) ingress_kernel(const uint8_t* __restrict__ gbuf, size_t gbytes, int iters, int mode,
+                                                         long long* __restrict__ cycles, long long* __restrict__ bytes) {
+  extern __shared__ __align__(1024) uint8_t esm[];
+  __shared__ uint64_t bar[4];
+  const int tid = threadIdx.x;
+  if (tid == 0) { for (int i = 0; i < 4; ++i) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i]))); } asm volatile("fence.mbarrier_init.release.cluster;"); }
+  __syncthreads();
+  const size_t slice = gbytes / gridDim.x / 32768 * 32768;
+  const uint8_t* mine = mode == 0 ? gbuf + (size_t)blockIdx.x * 262144u : gbuf + (size_t)blockIdx.x * slice;
+  const size_t span = mode == 0 ? 262144u : slice;
+  const long long t0 = clock64();
+  if (tid == 0) {
+    size_t off = 0;
+    for (int it = 0; it < iters + 4; ++it) {
+      const int b = it & 3;
+      if (it >= 4) {
+        uint32_t done = 0, ph = ((it >> 2) - 1) & 1;
+        while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&bar[b])), "r"(ph) : "memory");
+      }
+      if (it < iters) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[b])), "r"(32768u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(esm + b * 32768)), "l"(mine + off), "r"(32768u), "r"(smem_u32(&bar[b])) : "memory");
+        off += 32768; if (off + 32768 > span) off = 0;
+      }
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) { cycles[blockIdx.x] = t1 - t0; bytes[blockIdx.x] = (long long)iters * 32768; }
+}
+
+extern "C" int ingress_run(const uint8_t* gbuf, size_t gbytes, int iters, int mode, int nblocks, long long* cycles, long long* bytes, void* stream) {
+  cudaFuncSetAttribute(ingress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024);
+  ingress_kernel<<<nblocks, 128, 131072 + 1024, (cudaStream_t)stream>>>(gbuf, gbytes, iters, mode, cycles, bytes);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int egress_run(uint8_t* gbuf, int iters, int mode, int nblocks, long long* cycles, long long* bytes, void* stream) {
+  cudaFuncSetAttribute(egress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024);
+  egress_kernel<<<nblocks, 512, 131072 + 1024, (cudaStream_t)stream>>>(gbuf, iters, mode, cycles, bytes);
+  return (int)cudaGetLastError();
+}

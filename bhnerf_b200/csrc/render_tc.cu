@@ -651,12 +651,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_fwd_kernel(PackedView v, FrameConsts fc, const uint8_t* __restrict__ ws, const float* __restrict__ t_frames,
               int Bt, float* __restrict__ e_out, uint8_t* __restrict__ acts, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
+#ifdef BH_TC_TIMING
+  const long long t_kernel0 = clock64();
+#endif
 #ifndef BH_EXP_NORANGE
   if (((const float*)(ws + TC_WS_CONST))[TC_C_RANGE] != 0.f)
     tc_fwd_body<NPASS, SAVE, true>(smem, v, fc, ws, t_frames, Bt, e_out, acts, status);
   else
 #endif
     tc_fwd_body<NPASS, SAVE, false>(smem, v, fc, ws, t_frames, Bt, e_out, acts, status);
+#ifdef BH_TC_TIMING
+  if (threadIdx.x == 0) {     // per-CTA record for scripts/tc_timing.py: cycles (in units of 1024) and the SM it ran on
+    uint32_t smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    ((uint32_t*)((uint8_t*)status + TC_WS_CONST))[710 + blockIdx.x] = ((uint32_t)((clock64() - t_kernel0) >> 10) << 10) | smid;
+  }
+#endif
 }
 
 

@@ -647,6 +647,9 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, 
     if (lane == 0) {
       uint32_t cnt = 0;
       bool ok = true;
+#ifdef BH_EXP_EVICT
+      const uint64_t pol_stream = l2_policy_evict_first();
+#endif
       BH_TIMING_T0 BH_TIMING_DECL(t_gfl) BH_TIMING_DECL(t_em)
       for (int it = 0; ok; ++it) {
         WgSeq sq;
@@ -688,8 +691,19 @@ wgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink* links, 
                                  : (j < 3) ? TC_SIMG_BYTES + TC_FIMG_BYTES / 2u
                                  : (j == 3) ? TC_FIMG_BYTES : TC_AIMG_BYTES;
           mbar_expect_tx(full, TC_SIMG_BYTES + b_bytes);
+#ifdef BH_EXP_EVICT
+          // saved activations are read once: evict-first, so that they do not push the cotangent ring out of L2
+          if (FUSED && j == 4) bulk_g2s_hint(dst, a_src, TC_SIMG_BYTES, full, pol_stream); else
+#endif
           bulk_g2s(dst, a_src, TC_SIMG_BYTES, full);
           uint8_t* bdst = dst + TC_SIMG_BYTES;
+#ifdef BH_EXP_EVICT
+          if (FUSED && j < 3) {
+            bulk_g2s_hint(bdst, act_tile + pb * pstride + (size_t)(2 - j) * lstride, TC_SIMG_BYTES, full, pol_stream);
+            if (j == 0) bulk_g2s(bdst + TC_SIMG_BYTES, f_src, TC_FIMG_BYTES, full);
+            else bulk_g2s(bdst + TC_SIMG_BYTES, f_src + TC_FIMG_BYTES / 2u, TC_FIMG_BYTES / 2u, full);
+          } else
+#endif
           if (j < 3) {
             bulk_g2s(bdst, act_tile + pb * pstride + (size_t)(2 - j) * lstride, TC_SIMG_BYTES, full);
             if (j == 0) bulk_g2s(bdst + TC_SIMG_BYTES, f_src, TC_FIMG_BYTES, full);
@@ -910,6 +924,8 @@ tc_bwd_fused_kernel(PackedView v, const uint8_t* __restrict__ ws, const float* _
   }
 }
 
+#include "render_tc_bwd7.cuh"
+
 int g_num_sms_b = 0;
 int num_sms_b() {
   if (g_num_sms_b == 0) {
@@ -937,6 +953,12 @@ int bwd_dgrad_per_cluster() {
   return nd;
 }
 
+bool bwd_v7_enabled() {                    // BHNERF_TC_BWD_V7=1 selects the second-generation fused pair (slower as measured: opt-in)
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("BHNERF_TC_BWD_V7"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+
 bool bwd_fused_enabled() {                 // BHNERF_TC_FUSED=0 selects the two-kernel backward (A/B measurements)
   static int on = -1;
   if (on < 0) { const char* e = getenv("BHNERF_TC_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -955,9 +977,31 @@ int launch_bwd(const PackedView& v, const void* ws, const float* d_images, int B
     size_t n = (size_t)Bt * v.n_pad;
     int grid = (int)((n + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
     uint32_t* dout_max = (uint32_t*)((uint8_t*)ws + TC_WS_CONST) + TC_C_DOUTMAX;
-    BH_CHECK_CUDA(cudaMemsetAsync(dout_max, 0, sizeof(uint32_t), st));
+    static_assert(TC_C_SCHED == TC_C_DOUTMAX + 1, "one memset clears both words");
+    BH_CHECK_CUDA(cudaMemsetAsync(dout_max, 0, 2 * sizeof(uint32_t), st));
     tc_dout_kernel<<<grid, 256, 0, st>>>(v, d_images, e_saved, Bt, dout, dout_max);
     BH_CHECK_CUDA(cudaGetLastError());
+  }
+  if (PL == 1 && bwd_fused_enabled() && bwd_v7_enabled() && !bh_tc_fast()) {
+    BhProfScope ps(BH_CAT_BWD, 1, st);
+    auto kern = tc_bwd_fused7_kernel;
+    BH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F7_SM_TOTAL));
+    static int max_cl7 = 0;
+    if (max_cl7 == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (num_sms_b() / 2)); cfg.blockDim = dim3(kDThreads); cfg.dynamicSmemBytes = F7_SM_TOTAL;
+      cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms_b() / 2; }
+      max_cl7 = n;
+    }
+    int ncl = (NT + 1) / 2; if (ncl > num_sms_b() / 2) ncl = num_sms_b() / 2; if (ncl > max_cl7) ncl = max_cl7;
+    kern<<<2 * ncl, kDThreads, F7_SM_TOTAL, st>>>(v, (const uint8_t*)ws, dout, Bt, (const uint8_t*)acts, (uint8_t*)delta_ws,
+                                                  d_params, status);
+    BH_CHECK_CUDA(cudaGetLastError());
+    return 0;
   }
   if (PL == 1 && bwd_fused_enabled()) {
     BhProfScope ps(BH_CAT_BWD, 1, st);

@@ -59,6 +59,7 @@ __host__ __device__ inline size_t tc_delta_bytes_per_frame(int n_pad, int PL) { 
 #define TC_C_B4 640
 #define TC_C_RANGE 641                   // != 0: the weights allow |h| > 65504, the forward epilogue tracks the range
 #define TC_C_DOUTMAX 700                 // uint32 bits of max |d loss / d o| of the current backward launch (tc_dout_kernel)
+#define TC_C_SCHED 701                   // next tile pair of the fused backward's dynamic schedule (zeroed with DOUTMAX)
 
 // Optional cycle accounting (-DBH_TC_TIMING): block 0 writes, per role, the cycles spent waiting vs working into
 // the workspace status words [8..20) (two int32 per counter).  Compiled out by default.
@@ -111,6 +112,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// the same with an L2 eviction-priority hint (createpolicy): streamed-once data should not push the cotangent ring out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
 

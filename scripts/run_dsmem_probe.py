@@ -42,10 +42,32 @@ def mixed(a_fmt, b_fmt):
         'bf16' if a_fmt else 'fp16', 'bf16' if b_fmt else 'fp16', rc, int(st.item()), err), flush=True)
 
 
+def egress2():
+    """are the DSMEM path and the L2 path out of an SM independent?"""
+    lib.egress2_run.restype = C.c_int
+    lib.egress2_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    gbuf = torch.zeros(74 * 262144, dtype=torch.uint8, device='cuda')
+    o2 = torch.zeros(4 * 74, dtype=torch.int64, device='cuda')
+    reps = 24
+    print('\nSM egress, 74 CTA pairs, %d x 32 KB per path:' % reps)
+    for flags, name in ((1, 'DSMEM alone'), (2, 'global (L2) alone'), (3, 'both at once')):
+        for _ in range(2):
+            o2.zero_()
+            rc = lib.egress2_run(flags, reps, 74, gbuf.data_ptr(), o2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        assert rc == 0
+        r = o2.view(74, 4).double()
+        nb = reps * 32768
+        line = '  %-20s' % name
+        if flags & 1: line += '  DSMEM %6.1f B/clk' % (nb / r[:, 0].mean().item())
+        if flags & 2: line += '  global %6.1f B/clk' % (nb / r[:, 1].mean().item())
+        print(line, flush=True)
+
 if __name__ == '__main__':
     for nt in (128, 256, 512, 1024):
         bw(0, nt, 64)
     for chunk in (32768, 8192, 2048, 512):
         bw(1, 128, 16, chunk)
+    egress2()
     for a, b in ((1, 1), (0, 0), (1, 0), (0, 1)):      # last: an illegal combination would poison the context
         mixed(a, b)

@@ -59,3 +59,30 @@ for f, name in FL.items():
         torch.cuda.synchronize()
     assert rc == 0, rc
     print('%-60s %12.0f' % (name, cyc.double().mean().item() / it2), flush=True)
+
+# ---- SM egress to an L2-resident region ----
+lib.egress_run.restype = C.c_int
+lib.egress_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+nbytes = torch.zeros(148, dtype=torch.int64, device='cuda')
+MODES = {0: 'st.global.v4 from 16 warps', 1: 'cp.async.bulk smem->global, one 32 KB copy at a time', 2: 'cp.async.bulk, four 32 KB copies in flight',
+         3: 'st.global + cp.async.bulk together', 4: 'cp.async.bulk, eight 16 KB copies from eight lanes'}
+print('\n%-60s %8s %14s' % ('SM egress to an L2-resident region', 'CTAs', 'B/clk per SM'))
+for nblk in (148, 74, 1):
+    for m, name in MODES.items():
+        for _ in range(2):
+            rc = lib.egress_run(gbuf.data_ptr(), 200, m, nblk, cyc.data_ptr(), nbytes.data_ptr(), st)
+            torch.cuda.synchronize()
+        assert rc == 0, rc
+        print('%-60s %8d %14.1f' % (name, nblk, (nbytes[:nblk].double() / cyc[:nblk].double()).mean().item()), flush=True)
+
+# ---- SM ingress ----
+lib.ingress_run.restype = C.c_int
+lib.ingress_run.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+print('\n%-60s %8s %14s' % ('SM ingress, cp.async.bulk global->smem, 4 x 32 KB in flight', 'CTAs', 'B/clk per SM'))
+for nblk in (148, 74, 1):
+    for m, name in ((0, 'L2-resident private 256 KB region'), (1, 'streaming a %d MB buffer (HBM)' % (gbuf.numel() >> 20))):
+        for _ in range(2):
+            rc = lib.ingress_run(gbuf.data_ptr(), gbuf.numel(), 800, m, nblk, cyc.data_ptr(), nbytes.data_ptr(), st)
+            torch.cuda.synchronize()
+        assert rc == 0, rc
+        print('%-60s %8d %14.1f' % (name, nblk, (nbytes[:nblk].double() / cyc[:nblk].double()).mean().item()), flush=True)

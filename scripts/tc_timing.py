@@ -44,3 +44,12 @@ for save in (False, True):
     print('save=%d rounds/CTA=%d' % (save, rounds))
     for n, i in names:
         print('   %-20s %12d cycles  (%8.0f per round)' % (n, val(i), val(i) / rounds))
+    rec = ws[256 + 710 * 4:256 + 858 * 4].view(torch.int32).cpu().numpy().astype(np.int64) & 0xffffffff
+    order = np.argsort(rec & 0x3ff)
+    print('   per CTA (sorted by SM id): k-cycles per round')
+    line = ''
+    for i in order:
+        line += ' %3d:%5.2f' % (rec[i] & 0x3ff, (rec[i] >> 10) * 1.024 / rounds)
+        if len(line) > 150:
+            print('    ' + line); line = ''
+    print('    ' + line)

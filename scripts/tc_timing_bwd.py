@@ -40,6 +40,9 @@ for it in range(3):
     ev[1].record()
     _, dI = engine.loss_image(images, c['target'], c['sigma'], c['offset'], 1.0, kind)
     torch.cuda.synchronize()
+    engine._workspaces[torch.cuda.current_device()][200:216] = 0      # the MAX-over-CTAs words
+    engine._workspaces[torch.cuda.current_device()][256 + 710 * 4:256 + 860 * 4] = 0
+    torch.cuda.synchronize()
     ev[1].record()
     g = engine.render_bwd(scene, params, tf, dI, e, acts, 'tc', max_workspace=40 * 2 ** 30)
     ev[2].record()
@@ -53,11 +56,18 @@ w = ws[:256].view(torch.int32).cpu().numpy().astype(np.int64)
 val = lambda i: int((w[i] & 0xffffffff) | (w[i + 1] << 32))
 rounds = (tiles + 2 * 74 - 1) // (2 * 74)
 names = [('dgrad mma: wait A', 20), ('dgrad mma: issue', 22), ('dgrad epi: top (delta3)', 24), ('dgrad epi: wait ring free', 26),
-         ('dgrad epi: publish', 28), ('dgrad epi: wait D', 30), ('dgrad epi: layer epilogue', 32), ('dgrad epi: loop total', 34),
-         ('wgrad prod: wait feat empty', 36), ('wgrad prod: wait ring full', 38), ('wgrad prod: wait stage empty', 40),
-         ('wgrad mma: wait feat full', 42), ('wgrad mma: wait stage full', 44), ('wgrad mma: issue', 46),
-         ('wgrad mma: loop total', 48)]
+         ('wgrad gen: wait buffer free', 28), ('dgrad epi: wait D', 30), ('dgrad epi: layer epilogue', 32), ('dgrad epi: loop total', 34),
+         ('wgrad mma: wait X (activations)', 36), ('wgrad prod: wait ring full', 38), ('wgrad prod: wait stage empty', 40),
+         ('wgrad mma: wait delta_3 (rebuilt)', 42), ('wgrad mma: wait Y (cotangents)', 44), ('wgrad mma: issue', 46),
+         ('wgrad mma: loop total', 48), ('dgrad epi: loop total, MAX over pairs', 50), ('kernel entry -> exit, MAX over CTAs', 52)]
 print('  rounds (tile pairs) per CTA pair = %d' % rounds)
 for n, i in names:
     print('   %-30s %12d cycles  (%8.0f per round)' % (n, val(i), val(i) / rounds))
 print('   grad norm %.6e' % float(g.norm()))
+
+rec = ws[256 + 710 * 4:256 + 858 * 4].view(torch.int32).cpu().numpy().astype(np.int64).reshape(74, 2)
+print('  per pair: (dgrad SM, wgrad SM) rounds, cycles per round')
+for p in range(74):
+    cyc, info = int(rec[p, 0]) << 6, int(rec[p, 1])
+    rd = (info >> 20) & 0xfff
+    print('   pair %2d  SM %3d %3d  rounds %4d  %7.0f cycles/round' % (p, info & 0x3ff, (info >> 10) & 0x3ff, rd, cyc / max(rd, 1)))

@@ -97,10 +97,9 @@ class NeRF_Predictor:
 
     def init_state(self, params, num_iters=5000, lr_init=1e-4, lr_final=1e-6, lr_inject=None, checkpoint_dir='',
                    device=None):
-        """network.py:171-189.  ``lr_inject`` (learnable t_injection) is dead code in the reference (:235)."""
-        if lr_inject:
-            raise NotImplementedError('lr_inject: the t_injection parameter is commented out in the reference '
-                                      '(bhnerf/network.py:235)')
+        """network.py:171-189.  ``lr_inject`` is accepted and changes nothing, exactly as in the reference: it adds an
+        ``optax.masked`` Adam for leaves named 't_injection' (:176-180), and no such leaf exists -- the learnable injection
+        time is commented out (:235) -- so every parameter still gets the lr_init -> lr_final schedule."""
         device = torch.device(device if device is not None else 'cuda')
         state = TrainState(self, flatten_params(params), num_iters, lr_init, lr_final, device)
         if checkpoint_dir:
@@ -180,10 +179,8 @@ class GRID_Predictor:
 
     def init_state(self, params, num_iters=5000, lr_init=1e-4, lr_final=1e-6, lr_inject=None, checkpoint_dir='',
                    device=None):
-        """network.py:287-303 (optax.adam + polynomial_schedule on the grid)."""
-        if lr_inject:
-            raise NotImplementedError('lr_inject: the t_injection parameter is commented out in the reference '
-                                      '(bhnerf/network.py:355)')
+        """network.py:287-303 (optax.adam + polynomial_schedule on the grid).  ``lr_inject``: accepted, a no-op as in the
+        reference (its masked Adam matches leaves named 't_injection'; the grid params have none, :292-296)."""
         device = torch.device(device if device is not None else 'cuda')
         state = TrainState(self, self._flatten(params), num_iters, lr_init, lr_final, device)
         if checkpoint_dir:

@@ -44,3 +44,24 @@ for name, fn in (('vis_fwd', lambda: engine.vis_fwd(A, img)), ('vis_bwd', lambda
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print('%s alone: %.3f ms, %.0f GB/s = %.2f of HBM peak' % (name, ms, alg / 2 / ms / 1e6, alg / 2 / ms / 1e6 / peak), flush=True)
+
+# ---- separable tensor-core DFT head (opt-in: the caller hands over (u, v) instead of the matrix) at the same shape ----
+NA = NB = 128
+uv = (torch.rand(Bt, V, 2, device='cuda', generator=g) - 0.5) * 0.4
+grid = (-20.0, 40.0 / NA, -20.0, 40.0 / NB)
+imgs = img.view(Bt, NA, NB)
+dvis = torch.view_as_complex(torch.randn(Bt, V, 2, device='cuda', generator=g))
+for name, fn in (('vis_dft_fwd', lambda: engine.vis_dft_fwd(uv, imgs, grid)),
+                 ('vis_dft_bwd', lambda: engine.vis_dft_bwd(uv, dvis, grid, NA, NB))):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    flop = 2.0 * 2 * Bt * V * NA * NB            # one complex-by-real GEMM: cos and sin parts
+    print('%s: %.3f ms for %d frames (explicit-matrix pass: %.3f ms of HBM time at peak), %.1f TFLOP/s algorithmic'
+          % (name, ms, Bt, 8.0 * V * P * Bt / peak / 1e6, flop / ms / 1e9), flush=True)

@@ -363,6 +363,13 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       long long t_loop = clock64() - t_loop0;
       BH_TIMING_STORE(status, 24, t_top) BH_TIMING_STORE(status, 26, t_gf) BH_TIMING_STORE(status, 28, t_pub)
       BH_TIMING_STORE(status, 30, t_wd) BH_TIMING_STORE(status, 32, t_ep) BH_TIMING_STORE(status, 34, t_loop)
+      if (FUSED) {   // per-pair record (scripts/tc_timing_bwd.py): loop cycles / 64 and the SM this dgrad CTA ran on
+        uint32_t smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        uint32_t* rec = (uint32_t*)((uint8_t*)status + TC_WS_CONST) + 710 + (blockIdx.x / 2) * 2;
+        rec[0] = (uint32_t)(t_loop >> 6);
+        rec[1] = smid | (smid + 1u) << 10 | ((uint32_t)((NT / 2 + ncta - 1 - cta) / ncta) << 20);
+        atomicMax((unsigned long long*)(status + 50), (unsigned long long)t_loop);
+      }
     }
 #endif
     // d b4 = sum dout (network.py:64 bias of the last Dense)

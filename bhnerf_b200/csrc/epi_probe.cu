@@ -247,6 +247,16 @@ __global__ void __launch_bounds__(512, 1) egress_kernel(uint8_t* __restrict__ gb
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       nb += 131072;
     }
+    if ((mode == 5 || mode == 6) && tid == 0) {     // 16 groups of two 4 KB copies; mode 5 waits for each group's read, mode 6 lets one group run ahead
+      for (int k = 0; k < 16; ++k) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + 131072 + k * 8192), "r"(smem_u32(esm + (k & 3) * 8192)), "r"(4096u) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + 131072 + k * 8192 + 4096), "r"(smem_u32(esm + (k & 3) * 8192 + 4096)), "r"(4096u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (mode == 5) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+      nb += 131072;
+    }
     if (mode == 4 && tid < 32) {            // 8 x 16 KB copies issued by 8 lanes
       if (tid < 8) {
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + 131072 + tid * 16384), "r"(smem_u32(esm + tid * 16384)), "r"(16384u) : "memory");
@@ -299,6 +309,56 @@ __global__ void __launch_bounds__(128, 1) ingress_kernel(const uint8_t* __restri
 extern "C" int ingress_run(const uint8_t* gbuf, size_t gbytes, int iters, int mode, int nblocks, long long* cycles, long long* bytes, void* stream) {
   cudaFuncSetAttribute(ingress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024);
   ingress_kernel<<<nblocks, 128, 131072 + 1024, (cudaStream_t)stream>>>(gbuf, gbytes, iters, mode, cycles, bytes);
+  return (int)cudaGetLastError();
+}
+
+// the same two store forms, but STREAMING: every CTA walks through its own slice of a buffer far larger than L2 (what the
+// forward's saved activations are): mode 0 = st.global.v4 from 16 warps, 1 = cp.async.bulk 2 x 4 KB per group, one group ahead,
+// 2 = cp.async.bulk 32 KB per group, one group ahead
+__global__ void __launch_bounds__(512, 1) egress_stream_kernel(uint8_t* __restrict__ gbuf, size_t gbytes, int iters, int mode,
+                                                               long long* __restrict__ cycles, long long* __restrict__ bytes) {
+  extern __shared__ __align__(1024) uint8_t esm[];
+  const int tid = threadIdx.x;
+  const size_t slice = gbytes / gridDim.x / 131072 * 131072;
+  uint8_t* mine = gbuf + (size_t)blockIdx.x * slice;
+  for (int i = tid; i < 131072 / 16; i += 512) reinterpret_cast<uint4*>(esm)[i] = make_uint4(i, tid, 3u, 4u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const long long t0 = clock64();
+  size_t off = 0;
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k)
+        *reinterpret_cast<uint4*>(mine + off + ((size_t)(k * 512 + tid) * 16u)) = make_uint4(it, k, tid, 7u);
+    } else if (tid == 0) {
+      if (mode == 1) {
+        for (int k = 0; k < 16; ++k) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + off + k * 8192), "r"(smem_u32(esm + (k & 3) * 8192)), "r"(4096u) : "memory");
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + off + k * 8192 + 4096), "r"(smem_u32(esm + (k & 3) * 8192 + 4096)), "r"(4096u) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+      } else {
+        for (int k = 0; k < 4; ++k) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mine + off + k * 32768), "r"(smem_u32(esm + k * 32768)), "r"(32768u) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+      }
+    }
+    off += 131072; if (off + 131072 > slice) off = 0;
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __threadfence();
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) { cycles[blockIdx.x] = t1 - t0; bytes[blockIdx.x] = (long long)iters * 131072; }
+}
+
+extern "C" int egress_stream_run(uint8_t* gbuf, size_t gbytes, int iters, int mode, int nblocks, long long* cycles, long long* bytes, void* stream) {
+  cudaFuncSetAttribute(egress_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024);
+  egress_stream_kernel<<<nblocks, 512, 131072 + 1024, (cudaStream_t)stream>>>(gbuf, gbytes, iters, mode, cycles, bytes);
   return (int)cudaGetLastError();
 }
 

@@ -65,7 +65,8 @@ lib.egress_run.restype = C.c_int
 lib.egress_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 nbytes = torch.zeros(148, dtype=torch.int64, device='cuda')
 MODES = {0: 'st.global.v4 from 16 warps', 1: 'cp.async.bulk smem->global, one 32 KB copy at a time', 2: 'cp.async.bulk, four 32 KB copies in flight',
-         3: 'st.global + cp.async.bulk together', 4: 'cp.async.bulk, eight 16 KB copies from eight lanes'}
+         3: 'st.global + cp.async.bulk together', 4: 'cp.async.bulk, eight 16 KB copies from eight lanes',
+         5: 'cp.async.bulk, 2 x 4 KB per group, wait_group.read 0 each', 6: 'cp.async.bulk, 2 x 4 KB per group, one group ahead'}
 print('\n%-60s %8s %14s' % ('SM egress to an L2-resident region', 'CTAs', 'B/clk per SM'))
 for nblk in (148, 74, 1):
     for m, name in MODES.items():
@@ -73,7 +74,8 @@ for nblk in (148, 74, 1):
             rc = lib.egress_run(gbuf.data_ptr(), 200, m, nblk, cyc.data_ptr(), nbytes.data_ptr(), st)
             torch.cuda.synchronize()
         assert rc == 0, rc
-        print('%-60s %8d %14.1f' % (name, nblk, (nbytes[:nblk].double() / cyc[:nblk].double()).mean().item()), flush=True)
+        bw = nbytes[:nblk].double() / cyc[:nblk].double()
+        print('%-60s %8d %14.1f   (min %.1f, max %.1f over the SMs)' % (name, nblk, bw.mean().item(), bw.min().item(), bw.max().item()), flush=True)
 
 # ---- SM ingress ----
 lib.ingress_run.restype = C.c_int
@@ -86,3 +88,17 @@ for nblk in (148, 74, 1):
             torch.cuda.synchronize()
         assert rc == 0, rc
         print('%-60s %8d %14.1f' % (name, nblk, (nbytes[:nblk].double() / cyc[:nblk].double()).mean().item()), flush=True)
+
+# ---- SM egress, STREAMING to a buffer far larger than L2 (write-allocate + eviction to HBM) ----
+lib.egress_stream_run.restype = C.c_int
+lib.egress_stream_run.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+print('\n%-60s %8s %14s' % ('SM egress, streaming through a %d MB buffer' % (gbuf.numel() >> 20), 'CTAs', 'B/clk per SM'))
+for nblk in (148, 74):
+    for m, name in ((0, 'st.global.v4 from 16 warps'), (1, 'cp.async.bulk, 2 x 4 KB per group, one group ahead'),
+                    (2, 'cp.async.bulk, 32 KB per group, one group ahead')):
+        for _ in range(2):
+            rc = lib.egress_stream_run(gbuf.data_ptr(), gbuf.numel(), 200, m, nblk, cyc.data_ptr(), nbytes.data_ptr(), st)
+            torch.cuda.synchronize()
+        assert rc == 0, rc
+        bw = nbytes[:nblk].double() / cyc[:nblk].double()
+        print('%-60s %8d %14.1f   (min %.1f, max %.1f over the SMs)' % (name, nblk, bw.mean().item(), bw.min().item(), bw.max().item()), flush=True)

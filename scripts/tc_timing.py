@@ -36,14 +36,14 @@ for save in (False, True):
         engine.render_fwd(scene, params, tf, 'tc', save_acts=save)
     torch.cuda.synchronize()
     ws = engine._workspaces[torch.cuda.current_device()]
-    w = ws[:128].view(torch.int32).cpu().numpy().astype(np.int64)
+    w = ws[:256].view(torch.int32).cpu().numpy().astype(np.int64)
     val = lambda i: int((w[i] & 0xffffffff) | (w[i + 1] << 32))
     names = [('mma: wait weights', 8), ('mma: wait A', 10), ('mma: issue+commit', 12), ('epi: features', 14),
-             ('epi: wait D', 16), ('epi: epilogue', 18)]
+             ('epi: wait D', 16), ('epi: epilogue', 18), ('epi: wait staging buffer (inside epilogue)', 36)]
     rounds = (16 * scene.n_pad // 128 + 2 * 148 - 1) // (2 * 148)
     print('save=%d rounds/CTA=%d' % (save, rounds))
     for n, i in names:
-        print('   %-20s %12d cycles  (%8.0f per round)' % (n, val(i), val(i) / rounds))
+        print('   %-44s %12d cycles  (%8.0f per round)' % (n, val(i), val(i) / rounds))
     rec = ws[256 + 710 * 4:256 + 858 * 4].view(torch.int32).cpu().numpy().astype(np.int64) & 0xffffffff
     order = np.argsort(rec & 0x3ff)
     print('   per CTA (sorted by SM id): k-cycles per round')

@@ -3,20 +3,24 @@
 //
 //   tc_dgrad_kernel : d images -> d o -> delta_3 .. delta_0 (pre-activation cotangents), one 128-sample tile per
 //                     slot, two slots ping-pong.  delta_{l-1} = (delta_l * W_l[:128]^T) .* (h_{l-1} > 0) runs on the
-//                     tensor cores with delta_l (bf16) as the TMEM A operand and the forward's weight images
-//                     read K-major (two passes: W hi + W lo planes; DESIGN.md s4 "x2w").  All three hidden
-//                     weight layers stay resident in shared memory (208 KB, loaded once per CTA).
+//                     tensor cores with delta_l as the TMEM A operand and weight images read K-major, two products per
+//                     layer (W hi + W lo planes).  One-plane plan (PL = 1, the benchmarked one): cotangents are fp16 with
+//                     ONE power-of-two scale per launch (tc_dout_kernel reduces max|d loss/d o|, tc_grad_scale) and the
+//                     chain reads the FORWARD's fp16 weight images; two-plane plan (PL = 2, steps below 2^16 evaluated
+//                     sample-frames): bf16 hi + lo planes of everything.  All three hidden weight layers stay resident
+//                     in shared memory (192 KB, loaded once per CTA).
 //   tc_wgrad_kernel : dW_l^T[n][k] = sum_s delta_l[s][n] * in_l[s][k] as MN-major x MN-major UMMAs over the sample
 //                     axis, accumulated in TMEM (496 of 512 columns) across all tiles of a persistent CTA; bias
-//                     gradients ride on the constant-one column of the feature image, dW4 on the aux image.
+//                     gradients ride on the constant-one column of the feature image, dW4 on the CUDA cores.
 //   tc_bwd_fused_kernel : both roles in ONE launch as a cluster of two CTAs (rank 0 = dgrad, rank 1 = wgrad) per SM
 //                     pair.  The delta images go from the dgrad CTA to its partner through a small per-pair ring in
 //                     global memory that stays L2-resident (74 pairs x 4 tile sets x 132 KB = 39 MB) instead of a
 //                     per-frame HBM buffer; the hand-shake is mbarriers in the PARTNER's shared memory (remote arrive,
-//                     acquire/release at cluster scope).  DSMEM itself is not the data path: measured 21 B/clk per
-//                     SM (scripts/run_dsmem_probe.py), half of what the pair needs.  The single-SM fusion does not
-//                     fit: the wgrad accumulators take 464 of 512 TMEM columns and the two-plane weights 208 of
-//                     227 KB of shared memory.
+//                     acquire/release at cluster scope).  DSMEM is not the data path: it shares the SM's ~30 B/clk way
+//                     out with the L2 stores (scripts/run_dsmem_probe.py).  The single-SM fusion does not fit: the wgrad
+//                     accumulators take 496 of 512 TMEM columns.
+//   tc_bwd_fused7_kernel (render_tc_bwd7.cuh, BHNERF_TC_BWD_V7=1): second generation of the pair, opt-in -- measured
+//                     slower in every variant (profiles/r2_bwd_experiments.md).
 #include <stdlib.h>
 #include "tc_common.cuh"
 

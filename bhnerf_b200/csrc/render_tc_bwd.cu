@@ -290,6 +290,9 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
             delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), douts * w4[2 * jj], douts * w4[2 * jj + 1], d[4 * gq + jj], dl[4 * gq + jj]);
+#ifdef BH_EXP_NOD3STORE     // timing experiment: delta_3 is not written to the ring (wrong results)
+          if (d[4 * gq] == 0x12345678u)
+#endif
           BH_DSTORE(del_tile[s] + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
           if (PL == 2)
             *reinterpret_cast<uint4*>(del_tile[s] + pstride + 3 * dls + off) =

@@ -89,6 +89,50 @@ def test_adam_known_answer():
     assert abs(O.polynomial_schedule(1000, 1e-4, 1e-6, 1, 100) - 1e-6) < 1e-18
 
 
+def test_adam_restatement_agrees_with_an_independent_implementation():
+    """optax is not installed, so the Adam + linear-schedule restatement (reference network.py:171-182) is additionally
+    pinned on an INDEPENDENT implementation of the same published update: torch.optim.Adam (same bias correction, eps
+    outside the square root) driven by a LambdaLR with the polynomial(power=1) schedule evaluated at the pre-increment
+    count, as optax does."""
+    rng = np.random.default_rng(3)
+    p0 = rng.standard_normal(50)
+    lr0, lr1, n = 3e-3, 1e-5, 7
+    tp = torch.tensor(p0, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([tp], lr=1.0, betas=(0.9, 0.999), eps=1e-8)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda k: O.polynomial_schedule(k, lr0, lr1, 1, n))
+    p, mu, nu = p0.copy(), np.zeros(50), np.zeros(50)
+    for k in range(10):                                   # runs past num_iters: the schedule clips at lr_final
+        g = np.sin(3.0 * p + k) * (1.0 + 0.1 * k)
+        p, mu, nu = O.adam_step(p, g, mu, nu, k, lr0, lr1, n)
+        opt.zero_grad()
+        tp.grad = torch.tensor(np.sin(3.0 * tp.detach().numpy() + k) * (1.0 + 0.1 * k))
+        opt.step(); sched.step()
+        np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-12, atol=1e-15)
+
+
+def test_mlp_gradient_restatement_agrees_with_finite_differences(geo):
+    """The oracle's parameter gradient is torch float64 autograd through the restated MLP / predictor / ray integral / loss;
+    a central finite difference of the oracle's OWN loss along random parameter directions is an independent check of the
+    pull-back (value_and_grad, reference network.py:617)."""
+    d = np.load(os.path.join(G, 'case_lc_QU.npz'))
+    params = O.unflatten_params(d['params_flat'])
+    prd = dict(scale=float(d['scale']), rmin=float(d['rmin']), rmax=float(d['rmax']), z_width=float(d['z_width']))
+    rt = dict(coords=geo['coords'], Omega=geo['Omega'], J=d['J'], g=geo['g'], dtau=geo['dtau'], Sigma=geo['Sigma'],
+              t_start_obs=float(d['t_start_obs']), t_geos=geo['t_geos'], t_injection=float(d['t_injection']))
+    args = ('image', 'lc', d['target'], d['sigma'], np.zeros_like(d['target']), d['t_frames'], rt, prd)
+    ref = O.value_and_grad(params, *args, time_dtype=torch.float64)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        v = rng.standard_normal(d['params_flat'].shape)
+        v /= np.linalg.norm(v)
+        h = 1e-5
+        lp = O.value_and_grad(O.unflatten_params(d['params_flat'] + h * v), *args, time_dtype=torch.float64)['loss']
+        lm = O.value_and_grad(O.unflatten_params(d['params_flat'] - h * v), *args, time_dtype=torch.float64)['loss']
+        fd = (lp - lm) / (2 * h)
+        an = float(np.dot(ref['grads'], v))
+        assert abs(fd - an) <= 1e-5 * max(abs(an), 1e-3 * np.linalg.norm(ref['grads'])), (fd, an)
+
+
 def test_param_flatten_roundtrip():
     p = O.trained_like_params(3)
     flat = O.flatten_params(p)

@@ -817,3 +817,32 @@ def test_eht_step_with_separable_dft_equals_the_explicit_matrix_step(dtype):
     assert abs(out[0][0] - out[1][0]) / abs(out[0][0]) < IMG_TOL
     assert np.abs(out[0][1] - out[1][1]).max() / np.abs(out[0][1]).max() < IMG_TOL
     assert np.abs(out[0][2] - out[1][2]).max() / 1e-3 < 2e-2            # Adam update ~ lr per parameter
+
+
+def test_empty_and_tiny_recovery_domain():
+    """Edge cases of the prepack (emission.fill_unsupervised_emission zeroes everything outside the domain, emission.py:370-373):
+    a recovery domain that contains no sample gives zero images, zero loss against a zero target and a zero gradient; one that
+    keeps 156 samples (two tiles, mostly padding) agrees between the two kernel families."""
+    from bhnerf_b200 import constants, engine
+    geo = np.load(os.path.join(G, 'kerr_a0.2_i60_16x16x32.npz'))
+    d = np.load(os.path.join(G, 'case_image_full.npz'))
+    params = torch.as_tensor(d['params_flat']).cuda()
+    tf = torch.as_tensor(d['t_frames'].astype(np.float32)).cuda()
+    zero = np.zeros_like(d['target']); one = np.ones_like(zero)
+
+    def scene(rmin, rmax, zw):
+        return engine.PackedScene(geo['coords'], geo['Omega'], 1.0, geo['g'], geo['dtau'], geo['Sigma'], geo['t_geos'],
+                                  float(d['t_start_obs']), float(d['t_injection']), float(d['scale']), rmin, rmax, zw,
+                                  constants.GM_c3(t_units='hr'))
+    sc = scene(50.0, 60.0, 1e-3)
+    assert sc.n_active == 0
+    for impl in ('simt', 'tc'):
+        loss, img, g = engine.train_step_image(sc, params, tf, zero, one, zero, 1.0, 'full', impl)
+        assert float(loss) == 0.0 and float(img.abs().max()) == 0.0 and float(g.abs().max()) == 0.0
+    sc = scene(float(d['rmin']), float(d['rmin']) + 0.3, 4.0)
+    assert 0 < sc.n_active < 256
+    res = {impl: [t.clone() for t in engine.train_step_image(sc, params, tf, zero, one, zero, 1.0, 'full', impl)]
+           for impl in ('simt', 'tc')}
+    assert engine.workspace_status(impl='tc')[:5] == [0, 0, 0, 0, 0]
+    for a, b, tol in zip(res['tc'], res['simt'], (1e-4, 1e-4, 1e-3)):
+        assert float((a - b).abs().max()) <= tol * float(b.abs().max())

@@ -41,7 +41,10 @@ constexpr uint32_t D_SM_W = 0;
 constexpr uint32_t D_SM_W4 = DW_BYTES;                             // 128 floats
 constexpr uint32_t D_SM_BARS = D_SM_W4 + 512;
 constexpr uint32_t D_SM_TOTAL = D_SM_BARS + 128;
-constexpr int kRingDepth = 4;                                      // tile sets per CTA pair in the global delta ring
+#ifndef BH_RING_DEPTH
+#define BH_RING_DEPTH 4
+#endif
+constexpr int kRingDepth = BH_RING_DEPTH;                          // tile sets per CTA pair in the global delta ring
 constexpr uint32_t TSET_BYTES = 4u * TC_SIMG_BYTES + TC_AIMG_BYTES; // delta_0..3 images + aux image of one tile
 enum { DB_WFULL = 0, DB_AREADY = 1, DB_DREADY = 3, DB_GFREE = 5 /* x kRingDepth, arrived by the wgrad CTA */ };
 // fused mode: where the partner CTA of the pair is
@@ -242,10 +245,75 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 #ifdef BH_TC_TIMING
     const long long t_loop0 = clock64();
 #endif
+    // ---- top of a tile: delta_3[j] = dout * W4[j] * (h3[j] > 0) -> ring set + TMEM operand of the slot, hand to the MMA warp.
+    // Compile-time variant -DBH_DGRAD_PIPELINE_TOP=1 (measured SLOWER, profiles/r2_bwd_experiments.md): the top of the NEXT
+    // round's tile of a slot runs right after the slot's last accumulator (layer 1) has been pulled into registers, before
+    // those values are packed and stored, so the tensor core already works on the next tile while this CTA finishes delta_0
+    // and hands the round over.  It does not pay because the round is bound by the epilogue warps' own serial work, not by
+    // the tensor pipe's idle time, and the earlier claim on a ring set couples the pair more tightly.
+    uint8_t* del_cur[2] = {nullptr, nullptr};
+    uint32_t rd_cur[2] = {0u, 0u};
+    auto do_top = [&](int r, int s, float dout_s, uint32_t mw) -> bool {
+      const int T = (r * ncta + cta) * 2 + s, b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
+      const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;
+      rd_cur[s] = (uint32_t)(2 * r + s) % kRingDepth;
+      del_cur[s] = FUSED ? link.ring + (size_t)rd_cur[s] * TSET_BYTES : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
+      uint8_t* aux = FUSED ? del_cur[s] + 4u * TC_SIMG_BYTES
+                           : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
+      if (FUSED) {       // ring set free: the partner has pulled tile rk - kRingDepth out of it
+        BH_TIMING_BEGIN
+        const bool good = wait_cluster(&bars[DB_GFREE + rd_cur[s]], (((uint32_t)(2 * r + s) / kRingDepth) & 1u) ^ 1u, ab);
+        BH_TIMING_END(t_gf)
+        if (!good) return false;
+      }
+      BH_TIMING_BEGIN
+      if (cgrp == 0) {
+        db4 += dout_s;
+        const float dh = __bfloat162float(__float2bfloat16_rn(dout_s));      // aux image: col 0 = hi, col 1 = lo part of dout
+        *reinterpret_cast<uint4*>(aux + sample_img_off(row, 0)) = make_uint4(pack_bf16x2(dh, dout_s - dh), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(aux + sample_img_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      uint32_t d[16], dl[16];
+      const float douts = dout_s * gscale;
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const uint32_t off = sample_img_off(row, cgrp * 4 + gq);
+        const float* w4 = w4s + (cgrp * 4 + gq) * 8;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), douts * w4[2 * jj], douts * w4[2 * jj + 1], d[4 * gq + jj], dl[4 * gq + jj]);
+#ifdef BH_EXP_NOD3STORE     // timing experiment: delta_3 is not written to the ring (wrong results)
+        if (d[4 * gq] == 0x12345678u)
+#endif
+        BH_DSTORE(del_cur[s] + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
+        if (PL == 2)
+          *reinterpret_cast<uint4*>(del_cur[s] + pstride + 3 * dls + off) =
+              make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
+      }
+      const uint32_t t_slot = t_row + (uint32_t)s * 256u;
+      tmem_st16(t_slot + 128u + (uint32_t)(cgrp * 16), d);
+      if (PL == 2) tmem_st16(t_slot + 192u + (uint32_t)(cgrp * 16), dl);
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
+      BH_TIMING_END(t_top)
+      return true;
+    };
+#ifndef BH_DGRAD_PIPELINE_TOP
+#define BH_DGRAD_PIPELINE_TOP 0
+#endif
+    if (BH_DGRAD_PIPELINE_TOP && NT > cta * 2) {          // prologue: the tops of the first round
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (ok && cta * 2 + s < NT) ok = do_top(0, s, dout_next[s], mk_next[s][3]);
+    }
     for (int r = 0; ok; ++r) {
       const int T0 = (r * ncta + cta) * 2;
       if (T0 >= NT) break;
       const bool has[2] = {true, T0 + 1 < NT};
+      const int T0n = ((r + 1) * ncta + cta) * 2;
+      const bool has_next[2] = {T0n < NT, T0n + 1 < NT};
       float dout[2];
       uint32_t mk[2][4];
       uint8_t* del_tile[2];
@@ -258,57 +326,14 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       }
       load_inputs(r + 1);
       const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
-      // ---- top of both tiles: delta_3[j] = dout * W4[j] * (h3[j] > 0)
+      if (!BH_DGRAD_PIPELINE_TOP) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (!has[s] || !ok) continue;
-        const int T = T0 + s, b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
-        rd[s] = (uint32_t)(2 * r + s) % kRingDepth;
-        del_tile[s] = FUSED ? link.ring + (size_t)rd[s] * TSET_BYTES : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
-        uint8_t* aux = FUSED ? del_tile[s] + 4u * TC_SIMG_BYTES
-                             : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
-        if (FUSED) {       // ring set free: the partner has pulled tile rk - kRingDepth out of it
-          BH_TIMING_BEGIN
-          ok = wait_cluster(&bars[DB_GFREE + rd[s]], (((uint32_t)(2 * r + s) / kRingDepth) & 1u) ^ 1u, ab);
-          BH_TIMING_END(t_gf)
-          if (!ok) break;
-        }
-        BH_TIMING_BEGIN
-        if (cgrp == 0) {
-          db4 += dout[s];
-          const float dh = __bfloat162float(__float2bfloat16_rn(dout[s]));      // aux image: col 0 = hi, col 1 = lo part of dout
-          *reinterpret_cast<uint4*>(aux + sample_img_off(row, 0)) = make_uint4(pack_bf16x2(dh, dout[s] - dh), 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(aux + sample_img_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        uint32_t d[16], dl[16];
-        const uint32_t mw = mk[s][3];
-        const float douts = dout[s] * gscale;
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const uint32_t off = sample_img_off(row, cgrp * 4 + gq);
-          const float* w4 = w4s + (cgrp * 4 + gq) * 8;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), douts * w4[2 * jj], douts * w4[2 * jj + 1], d[4 * gq + jj], dl[4 * gq + jj]);
-#ifdef BH_EXP_NOD3STORE     // timing experiment: delta_3 is not written to the ring (wrong results)
-          if (d[4 * gq] == 0x12345678u)
-#endif
-          BH_DSTORE(del_tile[s] + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
-          if (PL == 2)
-            *reinterpret_cast<uint4*>(del_tile[s] + pstride + 3 * dls + off) =
-                make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
-        }
-        const uint32_t t_slot = t_row + (uint32_t)s * 256u;
-        tmem_st16(t_slot + 128u + (uint32_t)(cgrp * 16), d);
-        if (PL == 2) tmem_st16(t_slot + 192u + (uint32_t)(cgrp * 16), dl);
-        tmem_wait_st();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
-        BH_TIMING_END(t_top)
-
+        for (int s = 0; s < 2; ++s)
+          if (has[s] && ok) ok = do_top(r, s, dout[s], mk[s][3]);
+        if (!ok) break;
       }
-      if (!ok) break;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) { del_tile[s] = del_cur[s]; rd[s] = rd_cur[s]; }
       // ---- the chain, alternating between the slots: D = delta_l * W_l^T  ->  delta_{l-1}
       for (int l = 3; l >= 1 && ok; --l) {
 #pragma unroll
@@ -323,10 +348,16 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           if (!ok) break;
           d_phase[s] ^= 1u;
           tc_fence_after_sync();
-          BH_TIMING_BEGIN
           uint32_t raw[32];
           tmem_ld32(t_slot + (uint32_t)(cgrp * 32), raw);
           tmem_wait_ld();
+          if (BH_DGRAD_PIPELINE_TOP && l == 1 && has_next[s]) {
+            // the slot's accumulator is in registers and its last product is complete: the next tile's operand may go in
+            tc_fence_before_sync();
+            ok = do_top(r + 1, s, dout_next[s], mk_next[s][3]);
+            if (!ok) break;
+          }
+          BH_TIMING_BEGIN
           uint32_t d[16], dl[16];
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {

@@ -253,21 +253,22 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
     // the tensor pipe's idle time, and the earlier claim on a ring set couples the pair more tightly.
     uint8_t* del_cur[2] = {nullptr, nullptr};
     uint32_t rd_cur[2] = {0u, 0u};
-    auto do_top = [&](int r, int s, float dout_s, uint32_t mw) -> bool {
+    // mode 0: everything; 1: TMEM operand + hand to the MMA warp only; 2: ring stores (delta_3, aux) + db4 only
+    auto do_top = [&](int r, int s, float dout_s, uint32_t mw, int mode) -> bool {
       const int T = (r * ncta + cta) * 2 + s, b = T / tiles_per_frame, tile = T - b * tiles_per_frame;
       const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;
       rd_cur[s] = (uint32_t)(2 * r + s) % kRingDepth;
       del_cur[s] = FUSED ? link.ring + (size_t)rd_cur[s] * TSET_BYTES : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
       uint8_t* aux = FUSED ? del_cur[s] + 4u * TC_SIMG_BYTES
                            : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
-      if (FUSED) {       // ring set free: the partner has pulled tile rk - kRingDepth out of it
+      if (FUSED && mode != 1) {       // ring set free: the partner has pulled tile rk - kRingDepth out of it
         BH_TIMING_BEGIN
         const bool good = wait_cluster(&bars[DB_GFREE + rd_cur[s]], (((uint32_t)(2 * r + s) / kRingDepth) & 1u) ^ 1u, ab);
         BH_TIMING_END(t_gf)
         if (!good) return false;
       }
       BH_TIMING_BEGIN
-      if (cgrp == 0) {
+      if (cgrp == 0 && mode != 1) {
         db4 += dout_s;
         const float dh = __bfloat162float(__float2bfloat16_rn(dout_s));      // aux image: col 0 = hi, col 1 = lo part of dout
         *reinterpret_cast<uint4*>(aux + sample_img_off(row, 0)) = make_uint4(pack_bf16x2(dh, dout_s - dh), 0u, 0u, 0u);
@@ -282,21 +283,25 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
           delta_pack<PL>(tc_mask_expand(mw, 4 * gq + jj), douts * w4[2 * jj], douts * w4[2 * jj + 1], d[4 * gq + jj], dl[4 * gq + jj]);
+        if (mode != 1) {
 #ifdef BH_EXP_NOD3STORE     // timing experiment: delta_3 is not written to the ring (wrong results)
-        if (d[4 * gq] == 0x12345678u)
+          if (d[4 * gq] == 0x12345678u)
 #endif
-        BH_DSTORE(del_cur[s] + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
-        if (PL == 2)
-          *reinterpret_cast<uint4*>(del_cur[s] + pstride + 3 * dls + off) =
-              make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
+          BH_DSTORE(del_cur[s] + 3 * dls + off, make_uint4(d[4 * gq], d[4 * gq + 1], d[4 * gq + 2], d[4 * gq + 3]));
+          if (PL == 2)
+            *reinterpret_cast<uint4*>(del_cur[s] + pstride + 3 * dls + off) =
+                make_uint4(dl[4 * gq], dl[4 * gq + 1], dl[4 * gq + 2], dl[4 * gq + 3]);
+        }
       }
-      const uint32_t t_slot = t_row + (uint32_t)s * 256u;
-      tmem_st16(t_slot + 128u + (uint32_t)(cgrp * 16), d);
-      if (PL == 2) tmem_st16(t_slot + 192u + (uint32_t)(cgrp * 16), dl);
-      tmem_wait_st();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
+      if (mode != 2) {
+        const uint32_t t_slot = t_row + (uint32_t)s * 256u;
+        tmem_st16(t_slot + 128u + (uint32_t)(cgrp * 16), d);
+        if (PL == 2) tmem_st16(t_slot + 192u + (uint32_t)(cgrp * 16), dl);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
+      }
       BH_TIMING_END(t_top)
       return true;
     };
@@ -306,7 +311,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
     if (BH_DGRAD_PIPELINE_TOP && NT > cta * 2) {          // prologue: the tops of the first round
 #pragma unroll
       for (int s = 0; s < 2; ++s)
-        if (ok && cta * 2 + s < NT) ok = do_top(0, s, dout_next[s], mk_next[s][3]);
+        if (ok && cta * 2 + s < NT) ok = do_top(0, s, dout_next[s], mk_next[s][3], 1);
     }
     for (int r = 0; ok; ++r) {
       const int T0 = (r * ncta + cta) * 2;
@@ -326,10 +331,10 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       }
       load_inputs(r + 1);
       const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
-      if (!BH_DGRAD_PIPELINE_TOP) {
+      {   // pipelined: the TMEM operand of these tiles went in during the previous round; their ring stores happen here
 #pragma unroll
         for (int s = 0; s < 2; ++s)
-          if (has[s] && ok) ok = do_top(r, s, dout[s], mk[s][3]);
+          if (has[s] && ok) ok = do_top(r, s, dout[s], mk[s][3], BH_DGRAD_PIPELINE_TOP ? 2 : 0);
         if (!ok) break;
       }
 #pragma unroll
@@ -354,7 +359,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           if (BH_DGRAD_PIPELINE_TOP && l == 1 && has_next[s]) {
             // the slot's accumulator is in registers and its last product is complete: the next tile's operand may go in
             tc_fence_before_sync();
-            ok = do_top(r + 1, s, dout_next[s], mk_next[s][3]);
+            ok = do_top(r + 1, s, dout_next[s], mk_next[s][3], 1);
             if (!ok) break;
           }
           BH_TIMING_BEGIN

@@ -261,7 +261,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn_relu(float lo, float hi) {
 // residual of the fp16 hi plane, x - float(hi), for both halves of a packed pair: ONE full-rate FMA-pipe instruction per
 // element (fma.rn.f32.f16 = FHFMA: hi * -1 + x, exact -- the residual has <= 13 significant bits).  The earlier form, a
 // mantissa mask (LOP3) + FADD per element, ran on the ALU pipe, which binds this epilogue: F2FP, LOP3, PRMT and HSET2 all
-// issue there at one warp-instruction per 2 cycles (profiles/r2_epi_probe.log).
+// issue there at one warp-instruction per 2 cycles (profiles/r2_sm_egress_ingress_probe.log).
 __device__ __forceinline__ void f16x2_residual(uint32_t hi, float x0, float x1, float& r0, float& r1) {
   asm("{\n\t.reg .b16 l, u, m;\n\tmov.b32 {l, u}, %2;\n\tmov.b16 m, 0xBC00;\n\t"
       "fma.rn.f32.f16 %0, l, m, %3;\n\tfma.rn.f32.f16 %1, u, m, %4;\n\t}"

@@ -299,8 +299,10 @@ def main():
         engine._dist_world = lambda: (None, 0, 1)
 
     def step_e2e():
-        dev_args = [a.to(dev, non_blocking=True) for a in host_args]
-        loss, st, images = step_fn(state, 'hr', kind, *dev_args, *rta.values(), 1.0, impl=impl)
+        # the API takes the HOST buffers, as the reference's does (TemporalBatchedArgs hands numpy arrays to the pmap'd step);
+        # every host -> device copy of the step (h2d bytes below) happens inside the call: the image steps stage their inputs
+        # into one pinned buffer, the eht step streams A under the render of the chunk it belongs to
+        loss, st, images = step_fn(state, 'hr', kind, *host_args, *rta.values(), 1.0, impl=impl)
         return float(loss.item())                      # device -> host read of the step's result
 
     for _ in range(3):

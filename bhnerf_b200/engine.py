@@ -257,6 +257,35 @@ def _c64(x, dev):
     return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.complex64)), device=dev)
 
 
+_copy_streams = {}
+
+
+def upload_async(x_host, dev):
+    """Host tensor -> device on a per-device COPY stream, so that the transfer overlaps whatever the current stream is
+    doing.  Returns (device tensor, event): the consumer calls ``wait_upload`` right before its first use.  A pinned source
+    makes the call return at once; a pageable one blocks the host for the staging copy but still overlaps the GPU work that
+    is already enqueued."""
+    dev = torch.device(dev)
+    key = _dev_key(dev)
+    cs = _copy_streams.get(key)
+    if cs is None:
+        cs = _copy_streams[key] = torch.cuda.Stream(device=dev)
+    x_host = x_host.contiguous()
+    with torch.cuda.stream(cs):
+        y = x_host.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+    return y, ev
+
+
+def wait_upload(y, ev):
+    """Make the current stream wait for an ``upload_async`` transfer; returns the device tensor."""
+    cur = torch.cuda.current_stream(y.device)
+    cur.wait_event(ev)
+    y.record_stream(cur)
+    return y
+
+
 def vis_fwd(A, images):
     """vis [Bt,V] complex64 = A[b] @ vec(I[b])  (bhnerf/network.py:542-544).  images [Bt,1,P] or [Bt,P]."""
     lib = _lib.load(); dev = images.device

@@ -414,7 +414,7 @@ def _vis_head(A, images, target, sigma, scale, dtype, want_grad=True):
     return loss, vis, dI
 
 
-def _eht_prepare(scene, target, sigma, A, dtype, Bt):
+def _eht_prepare(scene, target, sigma, A, dtype, Bt, keep_host=False):
     """Shape checks of loss_fn_eht (network.py:542-559) and the flattening the C ABI takes.  The reference multiplies
     ``A (nt, [npol,] nvis, npix)`` with the image vectors ``(nt, [npol,] npix, 1)`` -- one DFT matrix per frame AND
     polarization (optimization.py:235-251 stacks them on axis 1) -- so the pol axis folds into the frame axis:
@@ -424,6 +424,11 @@ def _eht_prepare(scene, target, sigma, A, dtype, Bt):
     if isinstance(A, SeparableDFT):
         if tuple(A.image_shape) != tuple(scene.image_shape):
             raise AttributeError('SeparableDFT image_shape {} does not match the rays {}'.format(A.image_shape, scene.image_shape))
+    elif keep_host and not (isinstance(A, torch.Tensor) and A.is_cuda):
+        # stays on the host (zero-copy view): gradient_step_eht uploads it chunk by chunk UNDER the render of the chunk
+        A = A if isinstance(A, torch.Tensor) else torch.as_tensor(np.asarray(A))
+        if A.dtype != torch.complex64:
+            A = A.to(torch.complex64)
     else:
         A = engine._c64(A, scene.device)
     tshape = tuple(np.shape(target)) if not isinstance(target, torch.Tensor) else tuple(target.shape)
@@ -740,20 +745,36 @@ def gradient_step_eht(state, t_units, dtype, target, sigma, A, t_frames, coords,
                        device=state.flat.device)
     tf = engine._dev_f32(utils.time_value(t_frames, t_units) if not isinstance(t_frames, torch.Tensor) else t_frames,
                          scene.device).reshape(-1)
-    A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel())
+    A = _eht_prepare(scene, target, sigma, A, dtype, tf.numel(), keep_host=True)
+    A_on_host = isinstance(A, torch.Tensor) and not A.is_cuda
     # the chi^2 is separable per frame: process frame chunks whose saved activations fit the workspace cap
     Bt = tf.numel()
     Bc = Bt if isinstance(pred, GRID_Predictor) else engine.frames_per_chunk(scene, Bt, impl)
+    if A_on_host and Bt >= 16:
+        # a host-resident A is the long pole (8 V P bytes per frame over PCIe): quarter-batch chunks let the upload of chunk
+        # k+1 run under the head and the backward of chunk k
+        Bc = min(Bc, max(8, -(-Bt // 4)))
     tgt = engine._c64(target, scene.device) if dtype == 'vis' else engine._dev_f32(target, scene.device)
     sig = _eht_sigma(sigma, tgt, scene.device)
     npol = A.shape[0] // Bt                                   # DFT matrices per frame (1, or one per Stokes channel)
     tgt, sig = _eht_rows(tgt, Bt * npol), _eht_rows(sig, Bt * npol)
     loss, grads, imgs = None, None, []
-    for b0 in range(0, Bt, Bc):
+    starts = list(range(0, Bt, Bc))
+    rows_of = lambda b0: slice(b0 * npol, min(b0 + Bc, Bt) * npol)
+    pending = {}                                              # chunk start -> (device A, copy event)
+    for k, b0 in enumerate(starts):
         sl = slice(b0, min(b0 + Bc, Bt))
-        rows = slice(b0 * npol, min(b0 + Bc, Bt) * npol)
+        rows = rows_of(b0)
         images, e, acts = pred._render_fwd(scene, state.flat, tf[sl], impl, save_acts=not isinstance(pred, GRID_Predictor))
-        A_c = A[rows].contiguous()
+        if A_on_host:
+            # the chunk's DFT matrices (25 MB per frame at the cfg3 shape) travel on a copy stream while the render of the
+            # chunk -- enqueued above -- runs, and the NEXT chunk's follow right behind, under this chunk's head + backward
+            for b1 in starts[k:k + 2]:
+                if b1 not in pending:
+                    pending[b1] = engine.upload_async(A[rows_of(b1)], scene.device)
+            A_c = engine.wait_upload(*pending.pop(b0))
+        else:
+            A_c = A[rows].contiguous()
         l, _, dI = _vis_head(A_c, images.reshape(A_c.shape[0], 1, scene.P), tgt[rows], sig[rows], float(scale), dtype)
         dI = dI.reshape(images.shape)
         g = pred._render_bwd(scene, state.flat, tf[sl], dI, e, acts, impl)

@@ -49,6 +49,9 @@ def parse():
     ap.add_argument('--frames', type=int, default=None, help='override the number of frames (debug)')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     ap.add_argument('--ensemble', action='store_true', help='cfg5: one independent model per GPU, no collective')
+    ap.add_argument('--vis-head', default='matrix', choices=['matrix', 'separable'],
+                    help="cfg3: 'matrix' = the explicit complex64 A of loss_fn_eht (HBM-bound batched GEMV); 'separable' = "
+                         "the same Fourier kernel handed over as baselines (u, v): separable DFT on the tensor cores")
     ap.add_argument('--max-workspace-gb', type=float, default=40.0)
     ap.add_argument('--cpu-frames', type=int, default=None, help='frames in the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -228,9 +231,14 @@ def main():
 
     # resident inputs for the kernel-path timing
     tf_d = torch.as_tensor(c['t_frames'], device=dev)
+    separable = kind == 'vis' and args.vis_head == 'separable'
     if kind == 'vis':
-        A_d = torch.as_tensor(c['Amat'], device=dev)
-        V = A_d.shape[1]
+        if separable:
+            A_d = network.SeparableDFT.from_fov(c['uv'], scene.image_shape, c['cfg']['fov'])
+            V = c['uv'].shape[1]
+        else:
+            A_d = torch.as_tensor(c['Amat'], device=dev)
+            V = A_d.shape[1]
         tgt_d = torch.as_tensor(c['target'], device=dev); sig_d = torch.as_tensor(c['sigma'], device=dev)
         Bc = engine.frames_per_chunk(scene, Bt, impl, max_workspace=ws_cap)
 
@@ -239,7 +247,8 @@ def main():
             for b0 in range(0, Bt, Bc):
                 sl = slice(b0, min(b0 + Bc, Bt))
                 images, e, acts = engine.render_fwd(scene, state.flat, tf_d[sl], impl, save_acts=True)
-                l, _, dI = engine.vis_head(A_d[sl], images, tgt_d[sl], sig_d[sl], 1.0, 'vis')
+                l, _, dI = network._vis_head(A_d[sl], images.reshape(-1, 1, P), tgt_d[sl], sig_d[sl], 1.0, 'vis')
+                dI = dI.reshape(images.shape)
                 g = engine.render_bwd(scene, state.flat, tf_d[sl], dI, e, acts, impl, max_workspace=ws_cap)
                 grads = g if grads is None else engine.add_inplace(grads, g)
                 loss = l if loss is None else engine.add_inplace(loss, l)
@@ -285,15 +294,16 @@ def main():
 
     # ---- timed region 2: end to end through the reference-facing API with HOST buffers ----
     if kind == 'vis':
-        ts = optimization.TrainStep.eht_arrays(c['t_frames'], c['target'], c['sigma'], c['Amat'], dtype='vis')
+        ts = optimization.TrainStep.eht_arrays(c['t_frames'], c['target'], c['sigma'], A_d if separable else c['Amat'], dtype='vis')
         step_fn = network.gradient_step_eht
     else:
         ts = optimization.TrainStep.image(c['t_frames'], c['target'].reshape((Bt, S) if kind == 'lc' else (Bt, S, P)),
                                           sigma=c['sigma'].reshape((Bt, S) if kind == 'lc' else (Bt, S, P)), dtype=kind)
         step_fn = network.gradient_step_image
     # pinned host staging of the per-step inputs (target, sigma, offset | A, t_frames)
-    host_args = [torch.as_tensor(np.ascontiguousarray(a)).pin_memory() for a in ts.args[0].args]
-    h2d = sum(a.numel() * a.element_size() for a in host_args)
+    host_args = [a if isinstance(a, network.SeparableDFT) else torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+                 for a in ts.args[0].args]
+    h2d = sum(a.uv.nbytes if isinstance(a, network.SeparableDFT) else a.numel() * a.element_size() for a in host_args)
     if args.ensemble and world > 1:          # independent models: the step must not look for peers
         network._dist = lambda: None
         engine._dist_world = lambda: (None, 0, 1)
@@ -381,7 +391,18 @@ def main():
                 'design_hbm_gbs': design_gbs, 'design_hbm_frac': design_gbs / hbm_peak,
                 'design_bytes_per_evaluated_sample': sp['design_bytes'],
                 'traffic': tr * eval_per_launch if tr else None}
-        if kind == 'vis' and ms_by['vis_head'] > 0:
+        if separable and ms_by['vis_head'] > 0:
+            # separable DFT on the tensor cores: nothing of size V x P is read; algorithmic work = one real-by-complex GEMM per
+            # direction (cos and sin parts): 2 directions x 2 parts x 2 V P flop per frame
+            head_flop = 8.0 * V * P * Bt
+            head_s = ms_by['vis_head'] * 1e-3 / args.steps
+            kernels['vis_dft'] = {'bound': 'tensor', 'ms_per_step': head_s * 1e3, 'achieved': head_flop / head_s / 1e12,
+                                  'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': head_flop / head_s / 1e12 / tensor_peak,
+                                  'traffic': None, 'explicit_matrix_hbm_floor_ms': 2 * 8.0 * V * P * Bt / hbm_peak / 1e6,
+                                  'note': 'latency-bound at this size: the whole head is %.0f MFLOP; the point is the %.1f GB of '
+                                          'A it does not read' % (head_flop / 1e6, 2 * 8.0 * V * P * Bt / 1e9),
+                                  'launches_per_step': int(cat_sc[CATS.index('vis_head')]) // args.steps}
+        elif kind == 'vis' and ms_by['vis_head'] > 0:
             # the visibility head is a batched GEMV over a per-frame complex64 A: algorithmic bytes = 8*V*P per frame per
             # pass, two passes (A I and A^H d_vis) -- SURVEY.md s8d; the second pass is served by the L2 (bhnerf_vis_head)
             head_bytes = 2 * 8.0 * V * P * Bt + 2 * 4.0 * P * Bt

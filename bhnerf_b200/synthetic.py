@@ -110,6 +110,7 @@ def make_config(name, seed=0, frame_offset=0.0, nt=None, inc=None):
         uv = rng.uniform(-0.25, 0.25, size=(c['nt'], V, 2)).astype(np.float32)
         ph = -2 * np.pi * (uv[..., 0:1] * xx.reshape(1, 1, -1) + uv[..., 1:2] * yy.reshape(1, 1, -1))
         out['Amat'] = (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64)
+        out['uv'] = uv                      # the same matrix as baselines: network.SeparableDFT.from_fov(uv, (A, B), fov)
         out['target'] = (rng.normal(0, 1, (c['nt'], V)) + 1j * rng.normal(0, 1, (c['nt'], V))).astype(np.complex64)
         out['sigma'] = np.full((c['nt'], V), c['sigma'], dtype=np.float32)
     out['offset'] = np.zeros_like(out['sigma'])

@@ -3,13 +3,14 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--kernels auto|simt|tc]
                   [--workload cfg2_lp_flare|cfg1_tutorial3|cfg3_ngeht|cfg4_highres|cfg5_alma] [--frames F]
-                  [--scaling weak|strong] [--ensemble]
+                  [--scaling weak|strong] [--ensemble] [--vis-head matrix|separable]
 
 One "step" = one fused fwd+bwd train step (render -> loss -> parameter gradient [-> all-reduce-mean over ranks]; the
 e2e leg adds Adam and goes through the reference-facing API with HOST buffers) over ALL frames of the workload.
 Default workload = BASELINE.json configs[1] (128x128 rays x 128 samples x 100 frames, Q/U lightcurve loss), which fits one
 GPU.  cfg3_ngeht times the visibility step (render -> per-frame DFT to V baselines -> chi^2 -> pull-back) and reports the
-HBM roofline of the visibility head next to the tensor roofline of the render kernels.
+HBM roofline of the visibility head next to the tensor roofline of the render kernels; with --vis-head separable the same
+Fourier kernel is handed over as baselines (u, v) and the head runs as a separable DFT on the tensor cores.
 
 Several ranks (one process per GPU, launched by torchrun):
   --scaling weak   (default) every rank renders its own frames of the workload: global batch = frames x N; the ranks

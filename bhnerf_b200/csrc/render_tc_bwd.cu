@@ -28,6 +28,15 @@ using namespace tc;
 
 namespace {
 
+// Per-hop trace of the hand-off chain (-DBH_TC_TRACE, scripts/tc_trace_bwd.py): CTA 0 logs the low 32 bits of the clock at
+// the hops of rounds 10 and 11 into the spare constant words 710.. of the workspace.  Compiled out by default.
+#ifdef BH_TC_TRACE
+#define BH_TRACE(idx) do { if (blockIdx.x == 0 && (r == 10 || r == 11)) { uint32_t _c; asm volatile("mov.u32 %0, %%clock;" : "=r"(_c)); \
+    ((uint32_t*)((uint8_t*)status + TC_WS_CONST))[710 + (idx)] = _c; } } while (0)
+#else
+#define BH_TRACE(idx) do { } while (0)
+#endif
+
 // =====================================================================================================
 // dgrad chain
 // =====================================================================================================
@@ -172,6 +181,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
             a_phase[s] ^= 1u;
             tc_fence_after_sync();
             const uint32_t td = tbase + (uint32_t)s * 256u, ta = td + 128u;
+            if (lane == 0) BH_TRACE(((r - 10) * 6 + (3 - l) * 2 + s) * 2);
             BH_TIMING_BEGIN
             if (elect_one()) {
               // B' [K'=n][N'=k] = W_l[k][n]: the forward-layout image read K-major (K' groups = column groups);
@@ -187,6 +197,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
               mma_commit_raw(&bars[DB_DREADY + s]);
             }
             __syncwarp();
+            if (lane == 0) BH_TRACE(((r - 10) * 6 + (3 - l) * 2 + s) * 2 + 1);
             BH_TIMING_END(t_is)
           }
         }
@@ -267,6 +278,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         BH_TIMING_END(t_gf)
         if (!good) return false;
       }
+      if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + s * 2);
       BH_TIMING_BEGIN
       if (cgrp == 0 && mode != 1) {
         db4 += dout_s;
@@ -302,6 +314,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
       }
+      if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + s * 2 + 1);
       BH_TIMING_END(t_top)
       return true;
     };
@@ -353,9 +366,11 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
           if (!ok) break;
           d_phase[s] ^= 1u;
           tc_fence_after_sync();
+          if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 4 + ((3 - l) * 2 + s) * 4);
           uint32_t raw[32];
           tmem_ld32(t_slot + (uint32_t)(cgrp * 32), raw);
           tmem_wait_ld();
+          if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 4 + ((3 - l) * 2 + s) * 4 + 1);
           if (BH_DGRAD_PIPELINE_TOP && l == 1 && has_next[s]) {
             // the slot's accumulator is in registers and its last product is complete: the next tile's operand may go in
             tc_fence_before_sync();
@@ -381,9 +396,11 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
             if (PL == 2) tmem_st16(t_slot + 192u + (uint32_t)(cgrp * 16), dl);
             tmem_wait_st();
             tc_fence_before_sync();
+            if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 4 + ((3 - l) * 2 + s) * 4 + 2);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[DB_AREADY + s]);
           }
+          if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 4 + ((3 - l) * 2 + s) * 4 + 3);
           BH_TIMING_END(t_ep)
         }
       }
@@ -396,9 +413,11 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         // right after its last epilogue: 13.6 k (the release waits for the fresh stores); this placement: 12.9 k.
         pub_addr[0] = link.peer_bars + rd[0] * 8u;
         if (has[1]) pub_addr[1] = link.peer_bars + rd[1] * 8u;
+        if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 28);
         BH_TIMING_BEGIN
         publish_both();
         BH_TIMING_END(t_pub)
+        if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 29);
       }
     }
 #ifdef BH_TC_TIMING

@@ -272,6 +272,7 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       del_cur[s] = FUSED ? link.ring + (size_t)rd_cur[s] * TSET_BYTES : deltas + (size_t)b * del_fs + (size_t)tile * TC_SIMG_BYTES;
       uint8_t* aux = FUSED ? del_cur[s] + 4u * TC_SIMG_BYTES
                            : deltas + (size_t)b * del_fs + pstride * PL + (size_t)tile * TC_AIMG_BYTES;
+      if (tid == 0 && s == 0) BH_TRACE(84 + (r - 10) * 4 + 2);
       if (FUSED && mode != 1) {       // ring set free: the partner has pulled tile rk - kRingDepth out of it
         BH_TIMING_BEGIN
         const bool good = wait_cluster(&bars[DB_GFREE + rd_cur[s]], (((uint32_t)(2 * r + s) / kRingDepth) & 1u) ^ 1u, ab);
@@ -342,7 +343,9 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
 #pragma unroll
         for (int l = 0; l < 4; ++l) mk[s][l] = mk_next[s][l];
       }
+      if (tid == 0) BH_TRACE(84 + (r - 10) * 4);
       load_inputs(r + 1);
+      if (tid == 0) BH_TRACE(84 + (r - 10) * 4 + 1);
       const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
       {   // pipelined: the TMEM operand of these tiles went in during the previous round; their ring stores happen here
 #pragma unroll

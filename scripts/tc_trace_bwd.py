@@ -35,7 +35,7 @@ for it in range(3):
     g = engine.render_bwd(scene, params, tf, dI, e, acts, 'tc', max_workspace=40 * 2 ** 30)
     torch.cuda.synchronize()
 ws = engine._workspaces[torch.cuda.current_device()]
-w = ws[256 + 710 * 4:256 + (710 + 84) * 4].view(torch.int32).cpu().numpy().astype(np.int64) & 0xffffffff
+w = ws[256 + 710 * 4:256 + (710 + 92) * 4].view(torch.int32).cpu().numpy().astype(np.int64) & 0xffffffff
 ev = []
 for r in range(2):
     for li, l in enumerate((3, 2, 1)):
@@ -55,6 +55,9 @@ for r in range(2):
             if l > 1:
                 ev.append((w[k + 2], 'EPI  r%d l%d s%d  packed, stored, operand in TMEM' % (10 + r, l, s)))
             ev.append((w[k + 3], 'EPI  r%d l%d s%d  %s' % (10 + r, l, s, 'handed to the MMA warp' if l > 1 else 'delta_0 stored')))
+    ev.append((w[84 + r * 4], 'EPI  r%d loop top' % (10 + r)))
+    ev.append((w[84 + r * 4 + 1], 'EPI  r%d next round\'s inputs requested' % (10 + r)))
+    ev.append((w[84 + r * 4 + 2], 'EPI  r%d top s0: before the ring-set wait' % (10 + r)))
     ev.append((w[base + 28], 'EPI  r%d hand-over to the wgrad CTA: start' % (10 + r)))
     ev.append((w[base + 29], 'EPI  r%d hand-over to the wgrad CTA: done' % (10 + r)))
 ev = [(t, n) for t, n in ev if t != 0]

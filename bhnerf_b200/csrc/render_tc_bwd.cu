@@ -346,6 +346,9 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
       if (tid == 0) BH_TRACE(84 + (r - 10) * 4);
       load_inputs(r + 1);
       if (tid == 0) BH_TRACE(84 + (r - 10) * 4 + 1);
+#ifdef BH_EXP_LATE_PUBLISH   // experiment: the previous round is handed over here, after its stores have had ~0.9 k cycles to drain
+      publish_both();
+#endif
       const size_t dls = FUSED ? (size_t)TC_SIMG_BYTES : lstride;          // layer stride of the delta images
       {   // pipelined: the TMEM operand of these tiles went in during the previous round; their ring stores happen here
 #pragma unroll
@@ -416,13 +419,18 @@ dgrad_role(uint8_t* smem, const int cta, const int ncta, const PairLink link, co
         // right after its last epilogue: 13.6 k (the release waits for the fresh stores); this placement: 12.9 k.
         pub_addr[0] = link.peer_bars + rd[0] * 8u;
         if (has[1]) pub_addr[1] = link.peer_bars + rd[1] * 8u;
+#ifndef BH_EXP_LATE_PUBLISH
         if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 28);
         BH_TIMING_BEGIN
         publish_both();
         BH_TIMING_END(t_pub)
         if (tid == 0) BH_TRACE(24 + (r - 10) * 30 + 29);
+#endif
       }
     }
+#ifdef BH_EXP_LATE_PUBLISH
+    publish_both();                        // the last round
+#endif
 #ifdef BH_TC_TIMING
     if (tid == 0) {
       long long t_loop = clock64() - t_loop0;
